@@ -1,0 +1,195 @@
+// nms_peaks.cuh -- K1: 3x3 heat-map NMS + ordered peak extraction + centroid refinement.
+//
+// Replaces find_peaks (/root/reference/evaluate.py:169-203), i.e. util.keypoint_heatmap_nms
+// (utils/util.py:177-183) followed by np.nonzero (:193) and util.refine_centroid (:186-211) per peak.
+//
+// One CTA per (image, part) plane.  The plane is streamed through shared memory in row bands of full
+// rows (one contiguous span each) with the 1-D bulk-copy engine, double buffered on two mbarriers, so
+// HBM is read exactly once per pixel and the 3x3 window reads hit shared memory.  Detection scans
+// float4 groups and rejects a group with one compare when none of its 4 values reaches thre1 (the
+// common case).  Peaks are appended unordered and then rank-sorted by raster index, which restores
+// np.nonzero's order exactly (peak ids depend on it).  Refinement re-reads the 5x5 box from L2.
+#pragma once
+
+#include "common.cuh"
+
+namespace spg {
+
+struct NmsArgs {
+    const float *heat;
+    int64_t img_stride, chan_stride;  // elements
+    int H, W, band_rows, radius, use_bulk, image_base;
+    float thr;                        // (float)thre1: torch compares in f32 (util.py:182)
+    Workspace ws;
+};
+
+constexpr int kNmsThreads = 256;
+
+__device__ __forceinline__ bool nms_is_peak(const float *buf, int lo, int H, int W, int y, int x, float v, float thr) {
+    // keep = (hmax == heat) & (heat >= thre); np.nonzero(heat * keep) drops exact zeros
+    if (!(v >= thr) || v == 0.0f) return false;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;  // reflect-pad-1 == window clipped to the image
+        const float *row = buf + (size_t)(yy - lo) * W;
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W) continue;
+            if (!(row[xx] <= v)) return false;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kNmsThreads) nms_peaks_kernel(NmsArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar[2];
+    __shared__ int s_count;
+
+    const Workspace &ws = a.ws;
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x % ws.K;
+    const int n_local = blockIdx.x / ws.K;
+    const int n = a.image_base + n_local;
+    const int H = a.H, W = a.W, br = a.band_rows;
+    const float *plane = a.heat + (int64_t)n_local * a.img_stride + (int64_t)c * a.chan_stride;
+
+    const size_t band_floats = (size_t)(br + 2) * W;
+    float *buf0 = reinterpret_cast<float *>(smem_raw);
+    float *buf1 = buf0 + ((band_floats + 31) & ~(size_t)31);
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(buf1 + ((band_floats + 31) & ~(size_t)31));
+    uint32_t *s_sorted = s_list + ws.capP;
+
+    const int nb = (H + br - 1) / br;
+    if (tid == 0) {
+        s_count = 0;
+        if (a.use_bulk) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            fence_mbar_init();
+        }
+    }
+    __syncthreads();
+
+    auto band_lo = [&](int b) { return max(b * br - 1, 0); };
+    auto band_hi = [&](int b) { return min((b + 1) * br + 1, H); };
+    auto issue = [&](int b) {  // one thread: bulk copy rows [lo, hi) of the plane into buffer b&1
+        const int lo = band_lo(b), hi = band_hi(b);
+        const uint32_t bytes = (uint32_t)(hi - lo) * W * sizeof(float);
+        mbar_expect_tx(&bar[b & 1], bytes);
+        bulk_g2s((b & 1) ? buf1 : buf0, plane + (size_t)lo * W, bytes, &bar[b & 1]);
+    };
+
+    if (a.use_bulk && tid == 0) issue(0);
+
+    for (int b = 0; b < nb; b++) {
+        float *buf = (b & 1) ? buf1 : buf0;
+        const int lo = band_lo(b), hi = band_hi(b);
+        if (a.use_bulk) {
+            if (tid == 0 && b + 1 < nb) issue(b + 1);  // the other buffer was released by the barrier below
+            mbar_wait(&bar[b & 1], (b >> 1) & 1);
+        } else {
+            const int cnt = (hi - lo) * W;
+            for (int i = tid; i < cnt; i += kNmsThreads) buf[i] = plane[(size_t)lo * W + i];
+            __syncthreads();
+        }
+        const int y0 = b * br, y1 = min(y0 + br, H);
+        if ((W & 3) == 0) {
+            const int W4 = W >> 2;
+            const int groups = (y1 - y0) * W4;
+            for (int g = tid; g < groups; g += kNmsThreads) {
+                const int r = g / W4, xq = g - r * W4;
+                const int y = y0 + r;
+                const float4 v4 = *reinterpret_cast<const float4 *>(buf + (size_t)(y - lo) * W + 4 * xq);
+                const float m = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
+                if (!(m >= a.thr)) continue;
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int x = 4 * xq + e;
+                    if (nms_is_peak(buf, lo, H, W, y, x, vv[e], a.thr)) {
+                        const int pos = atomicAdd(&s_count, 1);
+                        if (pos < ws.capP) s_list[pos] = (uint32_t)(y * W + x);
+                    }
+                }
+            }
+        } else {
+            const int cnt = (y1 - y0) * W;
+            for (int i = tid; i < cnt; i += kNmsThreads) {
+                const int r = i / W, x = i - r * W;
+                const int y = y0 + r;
+                const float v = buf[(size_t)(y - lo) * W + x];
+                if (nms_is_peak(buf, lo, H, W, y, x, v, a.thr)) {
+                    const int pos = atomicAdd(&s_count, 1);
+                    if (pos < ws.capP) s_list[pos] = (uint32_t)(y * W + x);
+                }
+            }
+        }
+        __syncthreads();  // band consumed: its buffer may be refilled, s_count/s_list visible
+    }
+
+    const int total = s_count;
+    const int np = min(total, ws.capP);
+    // rank sort by raster index == np.nonzero order (evaluate.py:193); indices are unique
+    for (int t = tid; t < np; t += kNmsThreads) {
+        const uint32_t mine = s_list[t];
+        int rank = 0;
+        for (int u = 0; u < np; u++) rank += s_list[u] < mine;
+        s_sorted[rank] = mine;
+    }
+    __syncthreads();
+
+    const size_t out_base = ((size_t)n * ws.K + c) * ws.capP;
+    const int R = a.radius;
+    for (int t = tid; t < np; t += kNmsThreads) {
+        const int lin = (int)s_sorted[t];
+        const int y = lin / W, x = lin - y * W;
+        double rx, ry;
+        float sc;
+        uint32_t anchor = ((uint32_t)y << 16) | (uint32_t)x;
+        if (y + R + 1 > H || y - R < 0 || x + R + 1 > W || x - R < 0) {
+            // util.py:201-202: the box leaves the image -> integer anchor, raw map value
+            rx = (double)x;
+            ry = (double)y;
+            sc = plane[(size_t)y * W + x];
+            anchor |= 0x80000000u;
+        } else {
+            // util.py:204-211.  np.mgrid's first grid varies along ROWS and is the one added to x.
+            float box[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
+            double wr[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
+            double wc[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
+            int m = 0;
+            for (int r = -R; r <= R; r++)
+                for (int q = -R; q <= R; q++) {
+                    const float bv = __ldg(plane + (size_t)(y + r) * W + (x + q));
+                    box[m] = bv;
+                    wr[m] = __dmul_rn((double)bv, (double)r);
+                    wc[m] = __dmul_rn((double)bv, (double)q);
+                    m++;
+                }
+            const float s32 = pairwise_sum<float>(box, m);
+            const double off_x = __ddiv_rn(pairwise_sum<double>(wr, m), (double)s32);
+            const double off_y = __ddiv_rn(pairwise_sum<double>(wc, m), (double)s32);
+            rx = __dadd_rn((double)x, off_x);
+            ry = __dadd_rn((double)y, off_y);
+            sc = __fdiv_rn(s32, (float)m);  // score_box.mean() stays f32
+        }
+        ws.peak_x[out_base + t] = rx;
+        ws.peak_y[out_base + t] = ry;
+        ws.peak_score[out_base + t] = sc;
+        ws.peak_anchor[out_base + t] = anchor;
+    }
+    if (tid == 0) {
+        ws.peak_count[(size_t)n * ws.K + c] = total;
+        if (total > ws.capP) atomicOr(&ws.status[n], kStPeakOverflow);
+    }
+}
+
+inline size_t nms_smem_bytes(int band_rows, int W, int capP) {
+    const size_t band_floats = (((size_t)(band_rows + 2) * W) + 31) & ~(size_t)31;
+    return 2 * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t);
+}
+
+}  // namespace spg

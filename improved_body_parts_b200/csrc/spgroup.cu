@@ -1,0 +1,568 @@
+// spgroup.cu -- C ABI (include/spgroup.h) over the sm_100a grouping kernels.
+//
+// Host-side runtime of the path: handle/workspace management, launch configuration, the chunked
+// host-buffer pipeline (H2D copy of chunk c+1 overlapped with the kernels of chunk c on two streams) and
+// the state transfer used by the stage-wise drop-in functions.  No torch, no CPU implementation: if the
+// device or a launch fails the call fails.
+#include "../../include/spgroup.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "assemble.cuh"
+#include "common.cuh"
+#include "limb_match.cuh"
+#include "limb_score.cuh"
+#include "nms_peaks.cuh"
+
+using namespace spg;
+
+static_assert(sizeof(spg_params) == sizeof(spg::Params), "spg_params layout");
+
+static thread_local std::string g_create_error;
+
+struct spg_handle {
+    spg_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    Workspace ws{};
+    std::vector<void *> allocs;
+    int32_t *d_limbs = nullptr;
+    int32_t *d_out_from_part = nullptr;
+    // staging for spg_group_host
+    void *in_heat = nullptr, *in_paf = nullptr;
+    size_t in_heat_bytes = 0, in_paf_bytes = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
+    std::string err;
+};
+
+namespace {
+
+int fail(spg_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SPG_CUDA(h, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail((h), SPG_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int dalloc(spg_handle *h, T **p, size_t count) {
+    void *q = nullptr;
+    SPG_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return SPG_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int check_dims(spg_handle *h, int n, int H, int W) {
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images %d outside [0, max_batch=%d]", n, h->cfg.max_batch);
+    if (H < 2 || W < 2 || H > h->cfg.max_h || W > h->cfg.max_w || H > 32767 || W > 32767)
+        return fail(h, SPG_E_INVALID, "map %dx%d outside [2, %dx%d]", H, W, h->cfg.max_h, h->cfg.max_w);
+    return SPG_OK;
+}
+
+int check_params(spg_handle *h, const spg_params *p) {
+    if (!p) return fail(h, SPG_E_INVALID, "params is NULL");
+    if (p->offset_radius < 0 || p->offset_radius > kMaxRefineRadius)
+        return fail(h, SPG_E_INVALID, "offset_radius %d outside [0, %d]", p->offset_radius, kMaxRefineRadius);
+    if (p->mid_num < 1) return fail(h, SPG_E_INVALID, "mid_num must be >= 1");
+    return SPG_OK;
+}
+
+// ---- stage launchers on absolute image range [base, base+n) with chunk-local input pointers ----
+int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t chan_stride, int base, int n, int H, int W,
+               const spg_params *p, cudaStream_t st) {
+    if (n == 0) return SPG_OK;
+    NmsArgs a{};
+    a.heat = heat;
+    a.img_stride = img_stride;
+    a.chan_stride = chan_stride;
+    a.H = H;
+    a.W = W;
+    a.band_rows = std::max(4, std::min(H, 4096 / W));
+    a.radius = p->offset_radius;
+    a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
+    a.image_base = base;
+    a.thr = (float)p->thre1;
+    a.ws = h->ws;
+    const size_t smem = nms_smem_bytes(a.band_rows, W, h->ws.capP);
+    if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "map width %d needs %zu B of shared memory per band", W, smem);
+    SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_peaks_kernel<<<n * h->ws.K, kNmsThreads, smem, st>>>(a);
+    h->launches++;
+    SPG_CUDA(h, cudaGetLastError());
+    return SPG_OK;
+}
+
+template <typename T>
+int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
+    const size_t plane_bytes = (size_t)a.H * a.W * sizeof(T);
+    const size_t staged = score_smem_bytes(plane_bytes, h->ws.capP);
+    const bool aligned = (plane_bytes % 16 == 0) && ((a.img_stride * sizeof(T)) % 16 == 0) && ((a.chan_stride * sizeof(T)) % 16 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.paf) & 15) == 0) && plane_bytes < (1u << 20);
+    const int grid = n * h->ws.L;
+    if (aligned && staged <= h->smem_optin) {
+        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+        limb_score_kernel<T, true><<<grid, kScoreThreads, staged, st>>>(a);
+    } else {  // plane larger than shared memory (or unaligned): sample through L2
+        const size_t smem = score_smem_bytes(0, h->ws.capP);
+        limb_score_kernel<T, false><<<grid, kScoreThreads, smem, st>>>(a);
+    }
+    h->launches++;
+    SPG_CUDA(h, cudaGetLastError());
+    return SPG_OK;
+}
+
+int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, int64_t chan_stride, int base, int n, int H,
+                 int W, double extent, const spg_params *p, cudaStream_t st) {
+    if (n == 0) return SPG_OK;
+    ScoreArgs a{};
+    a.paf = paf;
+    a.img_stride = img_stride;
+    a.chan_stride = chan_stride;
+    a.H = H;
+    a.W = W;
+    a.image_base = base;
+    a.mid_num = p->mid_num;
+    a.image_extent = extent;
+    a.thre2 = p->thre2;
+    a.connect_ration = p->connect_ration;
+    a.ws = h->ws;
+    return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);
+}
+
+int launch_match(spg_handle *h, int base, int n, cudaStream_t st) {
+    if (n == 0) return SPG_OK;
+    MatchArgs a{};
+    a.n_images = n;
+    a.image_base = base;
+    a.ws = h->ws;
+    const int warps = n * h->ws.L;
+    const int blocks = (warps * 32 + kMatchThreads - 1) / kMatchThreads;
+    limb_match_kernel<<<blocks, kMatchThreads, 0, st>>>(a);
+    h->launches++;
+    SPG_CUDA(h, cudaGetLastError());
+    return SPG_OK;
+}
+
+int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStream_t st) {
+    if (n == 0) return SPG_OK;
+    AssembleArgs a{};
+    a.n_images = n;
+    a.image_base = base;
+    a.len_rate = p->len_rate;
+    a.connection_tole = p->connection_tole;
+    a.min_mean_score = p->min_mean_score;
+    a.remove_recon = p->remove_recon;
+    a.min_parts = p->min_parts;
+    a.ws = h->ws;
+    const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR);
+    SPG_CUDA(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_kernel<<<n, kAssembleThreads, smem, st>>>(a);
+    h->launches++;
+    SPG_CUDA(h, cudaGetLastError());
+    return SPG_OK;
+}
+
+int run_all(spg_handle *h, const float *heat, int64_t his, int64_t hcs, const void *paf, int dtype, int64_t pis, int64_t pcs,
+            int base, int n, int H, int W, double extent, const spg_params *p, cudaStream_t st) {
+    int rc;
+    SPG_CUDA(h, cudaMemsetAsync(h->ws.status + base, 0, sizeof(uint32_t) * (size_t)n, st));
+    if ((rc = launch_nms(h, heat, his, hcs, base, n, H, W, p, st))) return rc;
+    if ((rc = launch_score(h, paf, dtype, pis, pcs, base, n, H, W, extent, p, st))) return rc;
+    if ((rc = launch_match(h, base, n, st))) return rc;
+    if ((rc = launch_assemble(h, base, n, p, st))) return rc;
+    return SPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spg_abi_version(void) { return SPG_ABI_VERSION; }
+
+const char *spg_last_error(const spg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int spg_create(const spg_config *cfg, spg_handle **out) {
+    if (!cfg || !out) return fail(nullptr, SPG_E_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->abi_version != SPG_ABI_VERSION) return fail(nullptr, SPG_E_INVALID, "ABI version %d != %d", cfg->abi_version, SPG_ABI_VERSION);
+    if (cfg->n_parts < 1 || cfg->n_parts > kMaxParts || cfg->n_limbs < 1 || cfg->n_limbs > kMaxLimbs || !cfg->limbs)
+        return fail(nullptr, SPG_E_INVALID, "n_parts in [1,%d], n_limbs in [1,%d], limbs non-NULL required", kMaxParts, kMaxLimbs);
+    if (cfg->n_out_joints < 0 || cfg->n_out_joints > kMaxOutJoints || (cfg->n_out_joints && !cfg->out_from_part))
+        return fail(nullptr, SPG_E_INVALID, "n_out_joints in [0,%d]", kMaxOutJoints);
+    if (cfg->max_peaks_per_part < 1 || cfg->max_peaks_per_part > kMaxCapPeaks)
+        return fail(nullptr, SPG_E_INVALID, "max_peaks_per_part in [1,%d]", kMaxCapPeaks);
+    if (cfg->max_person_rows < 1 || cfg->max_person_rows > kMaxCapRows)
+        return fail(nullptr, SPG_E_INVALID, "max_person_rows in [1,%d]", kMaxCapRows);
+    if (cfg->max_cands_per_limb < 1 || cfg->max_batch < 1 || cfg->max_h < 2 || cfg->max_w < 2)
+        return fail(nullptr, SPG_E_INVALID, "max_cands_per_limb, max_batch >= 1 and max_h, max_w >= 2 required");
+    for (int k = 0; k < cfg->n_limbs * 2; k++)
+        if (cfg->limbs[k] < 0 || cfg->limbs[k] >= cfg->n_parts) return fail(nullptr, SPG_E_INVALID, "limb table entry %d out of range", k);
+    for (int g = 0; g < cfg->n_out_joints; g++)
+        if (cfg->out_from_part[g] < 0 || cfg->out_from_part[g] >= cfg->n_parts) return fail(nullptr, SPG_E_INVALID, "out_from_part[%d] out of range", g);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, SPG_E_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SPG_E_INVALID, "device %d outside [0,%d)", cfg->device, ndev);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, SPG_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, SPG_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    spg_handle *h = new (std::nothrow) spg_handle();
+    if (!h) return fail(nullptr, SPG_E_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->cfg.limbs = nullptr;
+    h->cfg.out_from_part = nullptr;
+    h->device = cfg->device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    DeviceGuard guard(h->device);
+
+    const size_t N = cfg->max_batch, K = cfg->n_parts, L = cfg->n_limbs, J = cfg->n_out_joints;
+    const size_t cP = cfg->max_peaks_per_part, cC = cfg->max_cands_per_limb, cR = cfg->max_person_rows;
+    Workspace &ws = h->ws;
+    ws.K = (int)K; ws.L = (int)L; ws.J = (int)J; ws.capP = (int)cP; ws.capC = (int)cC; ws.capR = (int)cR; ws.max_batch = (int)N;
+    int rc = SPG_OK;
+    auto A = [&](int r) { if (rc == SPG_OK) rc = r; };
+    A(dalloc(h, &h->d_limbs, L * 2));
+    A(dalloc(h, &h->d_out_from_part, J));
+    A(dalloc(h, &ws.peak_x, N * K * cP));
+    A(dalloc(h, &ws.peak_y, N * K * cP));
+    A(dalloc(h, &ws.peak_score, N * K * cP));
+    A(dalloc(h, &ws.peak_anchor, N * K * cP));
+    A(dalloc(h, &ws.peak_count, N * K));
+    A(dalloc(h, &ws.cand_prio, N * L * cC));
+    A(dalloc(h, &ws.cand_score, N * L * cC));
+    A(dalloc(h, &ws.cand_ij, N * L * cC));
+    A(dalloc(h, &ws.cand_count, N * L));
+    A(dalloc(h, &ws.conn_ij, N * L * cP));
+    A(dalloc(h, &ws.conn_score, N * L * cP));
+    A(dalloc(h, &ws.conn_norm, N * L * cP));
+    A(dalloc(h, &ws.conn_count, N * L));
+    A(dalloc(h, &ws.subset, N * cR * (K + 2) * 2));
+    A(dalloc(h, &ws.n_persons, N));
+    A(dalloc(h, &ws.people_xy, N * cR * std::max<size_t>(J, 1) * 2));
+    A(dalloc(h, &ws.people_score, N * cR));
+    A(dalloc(h, &ws.status, N));
+    if (rc == SPG_OK && cudaMemcpy(h->d_limbs, cfg->limbs, sizeof(int32_t) * L * 2, cudaMemcpyHostToDevice) != cudaSuccess) rc = SPG_E_CUDA;
+    if (rc == SPG_OK && J && cudaMemcpy(h->d_out_from_part, cfg->out_from_part, sizeof(int32_t) * J, cudaMemcpyHostToDevice) != cudaSuccess) rc = SPG_E_CUDA;
+    if (rc == SPG_OK && cudaMemset(ws.status, 0, sizeof(uint32_t) * N) != cudaSuccess) rc = SPG_E_CUDA;
+    if (rc == SPG_OK && cudaMemset(ws.peak_count, 0, sizeof(int32_t) * N * K) != cudaSuccess) rc = SPG_E_CUDA;
+    for (int s = 0; s < 2 && rc == SPG_OK; s++)
+        if (cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = SPG_E_CUDA;
+    if (rc != SPG_OK) {
+        g_create_error = h->err.empty() ? "device allocation failed" : h->err;
+        spg_destroy(h);
+        return rc;
+    }
+    ws.limbs = h->d_limbs;
+    ws.out_from_part = h->d_out_from_part;
+    *out = h;
+    return SPG_OK;
+}
+
+void spg_destroy(spg_handle *h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->in_heat) cudaFree(h->in_heat);
+    if (h->in_paf) cudaFree(h->in_paf);
+    for (auto &s : h->streams)
+        if (s) cudaStreamDestroy(s);
+    delete h;
+}
+
+int spg_get_device_view(const spg_handle *h, spg_device_view *v) {
+    if (!h || !v) return SPG_E_INVALID;
+    const Workspace &ws = h->ws;
+    v->max_batch = ws.max_batch; v->n_parts = ws.K; v->n_limbs = ws.L; v->n_out_joints = ws.J;
+    v->cap_peaks = ws.capP; v->cap_cands = ws.capC; v->cap_rows = ws.capR;
+    v->peak_x = ws.peak_x; v->peak_y = ws.peak_y; v->peak_score = ws.peak_score; v->peak_anchor = ws.peak_anchor;
+    v->peak_count = ws.peak_count;
+    v->conn_ij = ws.conn_ij; v->conn_score = ws.conn_score; v->conn_norm = ws.conn_norm; v->conn_count = ws.conn_count;
+    v->cand_count = ws.cand_count;
+    v->subset = ws.subset; v->n_persons = ws.n_persons; v->people_xy = ws.people_xy; v->people_score = ws.people_score;
+    v->status = ws.status;
+    return SPG_OK;
+}
+
+int64_t spg_launch_count(const spg_handle *h) { return h ? h->launches : 0; }
+
+// ---- stages ------------------------------------------------------------------------------------
+int spg_nms_peaks(spg_handle *h, const float *heat, int64_t image_stride, int64_t chan_stride, int32_t n, int32_t H, int32_t W,
+                  const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (!heat && n > 0) return fail(h, SPG_E_INVALID, "heat_dev is NULL");
+    int rc;
+    if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SPG_CUDA(h, cudaMemsetAsync(h->ws.status, 0, sizeof(uint32_t) * (size_t)n, st));
+    if ((rc = launch_nms(h, heat, image_stride, chan_stride, 0, n, H, W, p, st))) return rc;
+    h->stage = 1;
+    return SPG_OK;
+}
+
+int spg_limb_score(spg_handle *h, const void *paf, int32_t dtype, int64_t image_stride, int64_t chan_stride, int32_t n, int32_t H,
+                   int32_t W, double extent, const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (!paf && n > 0) return fail(h, SPG_E_INVALID, "paf_dev is NULL");
+    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    if (h->stage < 1) return fail(h, SPG_E_STATE, "spg_limb_score needs peaks (spg_nms_peaks or spg_upload_peaks) first");
+    int rc;
+    if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    if ((rc = launch_score(h, paf, dtype, image_stride, chan_stride, 0, n, H, W, extent, p, static_cast<cudaStream_t>(stream)))) return rc;
+    h->stage = std::max(h->stage, 2);
+    return SPG_OK;
+}
+
+int spg_limb_match(spg_handle *h, int32_t n, const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (h->stage < 2) return fail(h, SPG_E_STATE, "spg_limb_match needs spg_limb_score first");
+    int rc;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    if ((rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    if ((rc = launch_match(h, 0, n, static_cast<cudaStream_t>(stream)))) return rc;
+    h->stage = std::max(h->stage, 3);
+    return SPG_OK;
+}
+
+int spg_assemble(spg_handle *h, int32_t n, const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (h->stage < 3) return fail(h, SPG_E_STATE, "spg_assemble needs connections (spg_limb_match or spg_upload_connections) first");
+    int rc;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    if ((rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    if ((rc = launch_assemble(h, 0, n, p, static_cast<cudaStream_t>(stream)))) return rc;
+    h->stage = 4;
+    return SPG_OK;
+}
+
+int spg_group_batch(spg_handle *h, const float *heat, int64_t his, int64_t hcs, const void *paf, int32_t dtype, int64_t pis, int64_t pcs,
+                    int32_t n, int32_t H, int32_t W, double extent, const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if ((!heat || !paf) && n > 0) return fail(h, SPG_E_INVALID, "heat_dev/paf_dev is NULL");
+    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    int rc;
+    if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    if ((rc = run_all(h, heat, his, hcs, paf, dtype, pis, pcs, 0, n, H, W, extent, p, static_cast<cudaStream_t>(stream)))) return rc;
+    h->stage = 4;
+    return SPG_OK;
+}
+
+int spg_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return SPG_E_INVALID;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? SPG_OK : SPG_E_CUDA;
+}
+int spg_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SPG_OK : SPG_E_CUDA; }
+
+int spg_group_host(spg_handle *h, const float *heat_host, const void *paf_host, int32_t dtype, int32_t n, int32_t H, int32_t W,
+                   double extent, const spg_params *p, int32_t *out_n, double *out_xy, double *out_score, uint32_t *out_status) {
+    if (!h) return SPG_E_INVALID;
+    if ((!heat_host || !paf_host) && n > 0) return fail(h, SPG_E_INVALID, "heat_host/paf_host is NULL");
+    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    int rc;
+    if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    const Workspace &ws = h->ws;
+    const size_t plane = (size_t)H * W;
+    const size_t esz = dtype == SPG_F64 ? 8 : 4;
+    const size_t heat_img = (size_t)ws.K * plane * sizeof(float), paf_img = (size_t)ws.L * plane * esz;
+    // chunk so that copy(c+1) overlaps kernels(c); keep at least ~8 chunks for large batches
+    const int chunk = std::max(1, std::min(n, std::max(8, n / 8)));
+    const size_t need_heat = 2 * (size_t)chunk * heat_img, need_paf = 2 * (size_t)chunk * paf_img;
+    if (h->in_heat_bytes < need_heat) {
+        if (h->in_heat) cudaFree(h->in_heat);
+        h->in_heat = nullptr; h->in_heat_bytes = 0;
+        SPG_CUDA(h, cudaMalloc(&h->in_heat, need_heat));
+        h->in_heat_bytes = need_heat;
+    }
+    if (h->in_paf_bytes < need_paf) {
+        if (h->in_paf) cudaFree(h->in_paf);
+        h->in_paf = nullptr; h->in_paf_bytes = 0;
+        SPG_CUDA(h, cudaMalloc(&h->in_paf, need_paf));
+        h->in_paf_bytes = need_paf;
+    }
+    const size_t RSJ = (size_t)ws.capR * ws.J * 2;
+    int ci = 0;
+    for (int base = 0; base < n; base += chunk, ci++) {
+        const int m = std::min(chunk, n - base);
+        cudaStream_t st = h->streams[ci & 1];
+        unsigned char *dh = static_cast<unsigned char *>(h->in_heat) + (size_t)(ci & 1) * chunk * heat_img;
+        unsigned char *dp = static_cast<unsigned char *>(h->in_paf) + (size_t)(ci & 1) * chunk * paf_img;
+        // stream order protects the staging buffers: chunk ci reuses the buffers of chunk ci-2 on the same stream
+        SPG_CUDA(h, cudaMemcpyAsync(dh, reinterpret_cast<const unsigned char *>(heat_host) + (size_t)base * heat_img, (size_t)m * heat_img, cudaMemcpyHostToDevice, st));
+        SPG_CUDA(h, cudaMemcpyAsync(dp, static_cast<const unsigned char *>(paf_host) + (size_t)base * paf_img, (size_t)m * paf_img, cudaMemcpyHostToDevice, st));
+        if ((rc = run_all(h, reinterpret_cast<const float *>(dh), (int64_t)ws.K * plane, (int64_t)plane, dp, dtype, (int64_t)ws.L * plane,
+                          (int64_t)plane, base, m, H, W, extent, p, st)))
+            return rc;
+        if (out_n) SPG_CUDA(h, cudaMemcpyAsync(out_n + base, ws.n_persons + base, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+        if (out_xy && ws.J) SPG_CUDA(h, cudaMemcpyAsync(out_xy + (size_t)base * RSJ, ws.people_xy + (size_t)base * RSJ, sizeof(double) * RSJ * m, cudaMemcpyDeviceToHost, st));
+        if (out_score) SPG_CUDA(h, cudaMemcpyAsync(out_score + (size_t)base * ws.capR, ws.people_score + (size_t)base * ws.capR, sizeof(double) * ws.capR * m, cudaMemcpyDeviceToHost, st));
+        if (out_status) SPG_CUDA(h, cudaMemcpyAsync(out_status + base, ws.status + base, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, st));
+    }
+    SPG_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+    SPG_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+    h->stage = 4;
+    return SPG_OK;
+}
+
+// ---- state transfer ------------------------------------------------------------------------------
+int spg_upload_peaks(spg_handle *h, int32_t img, const int32_t *part_count, const double *x, const double *y, const float *score, void *stream) {
+    if (!h || !part_count) return SPG_E_INVALID;
+    if (img < 0 || img >= h->cfg.max_batch) return fail(h, SPG_E_INVALID, "image_index out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace &ws = h->ws;
+    size_t off = 0;
+    for (int c = 0; c < ws.K; c++) {
+        const int m = part_count[c];
+        if (m < 0 || m > ws.capP) return fail(h, SPG_E_INVALID, "part %d has %d peaks; capacity is %d", c, m, ws.capP);
+        const size_t dst = ((size_t)img * ws.K + c) * ws.capP;
+        if (m) {
+            if (!x || !y || !score) return fail(h, SPG_E_INVALID, "peak arrays are NULL");
+            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_x + dst, x + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_y + dst, y + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_score + dst, score + off, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+        }
+        off += m;
+    }
+    SPG_CUDA(h, cudaMemcpyAsync(ws.peak_count + (size_t)img * ws.K, part_count, sizeof(int32_t) * ws.K, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaMemsetAsync(ws.status + img, 0, sizeof(uint32_t), st));
+    SPG_CUDA(h, cudaStreamSynchronize(st));  // the host arrays may be temporaries
+    h->stage = std::max(h->stage, 1);
+    return SPG_OK;
+}
+
+int spg_upload_connections(spg_handle *h, int32_t img, const int32_t *conn_count, const int32_t *ij, const double *score, const double *norm, void *stream) {
+    if (!h || !conn_count) return SPG_E_INVALID;
+    if (img < 0 || img >= h->cfg.max_batch) return fail(h, SPG_E_INVALID, "image_index out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace &ws = h->ws;
+    std::vector<uint32_t> packed;
+    size_t off = 0;
+    for (int k = 0; k < ws.L; k++) {
+        const int m = conn_count[k];
+        if (m > ws.capP) return fail(h, SPG_E_INVALID, "limb %d has %d connections; capacity is %d", k, m, ws.capP);
+        if (m <= 0) continue;
+        if (!ij || !score || !norm) return fail(h, SPG_E_INVALID, "connection arrays are NULL");
+        packed.resize(m);
+        for (int r = 0; r < m; r++) {
+            const int32_t i = ij[(off + r) * 2], j = ij[(off + r) * 2 + 1];
+            if (i < 0 || j < 0 || i >= ws.capP || j >= ws.capP) return fail(h, SPG_E_INVALID, "connection index out of range");
+            packed[r] = ((uint32_t)i << 16) | (uint32_t)j;
+        }
+        const size_t dst = ((size_t)img * ws.L + k) * ws.capP;
+        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_ij + dst, packed.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, st));
+        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_score + dst, score + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_norm + dst, norm + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        SPG_CUDA(h, cudaStreamSynchronize(st));  // `packed` is reused
+        off += m;
+    }
+    SPG_CUDA(h, cudaMemcpyAsync(ws.conn_count + (size_t)img * ws.L, conn_count, sizeof(int32_t) * ws.L, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaStreamSynchronize(st));
+    h->stage = std::max(h->stage, 3);
+    return SPG_OK;
+}
+
+#define SPG_D2H(dst, src, count)                                                                                          \
+    do {                                                                                                                  \
+        if (dst) SPG_CUDA(h, cudaMemcpyAsync((dst), (src), sizeof(*(dst)) * (size_t)(count), cudaMemcpyDeviceToHost, st)); \
+    } while (0)
+
+int spg_download_peaks(spg_handle *h, int32_t n, int32_t *peak_count, double *x, double *y, float *score, uint32_t *anchor, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace &ws = h->ws;
+    const size_t m = (size_t)n * ws.K * ws.capP;
+    SPG_D2H(peak_count, ws.peak_count, (size_t)n * ws.K);
+    SPG_D2H(x, ws.peak_x, m);
+    SPG_D2H(y, ws.peak_y, m);
+    SPG_D2H(score, ws.peak_score, m);
+    SPG_D2H(anchor, ws.peak_anchor, m);
+    SPG_CUDA(h, cudaStreamSynchronize(st));
+    return SPG_OK;
+}
+
+int spg_download_connections(spg_handle *h, int32_t n, int32_t *conn_count, int32_t *cand_count, uint32_t *ij, double *score, double *norm, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace &ws = h->ws;
+    const size_t m = (size_t)n * ws.L * ws.capP;
+    SPG_D2H(conn_count, ws.conn_count, (size_t)n * ws.L);
+    SPG_D2H(cand_count, ws.cand_count, (size_t)n * ws.L);
+    SPG_D2H(ij, ws.conn_ij, m);
+    SPG_D2H(score, ws.conn_score, m);
+    SPG_D2H(norm, ws.conn_norm, m);
+    SPG_CUDA(h, cudaStreamSynchronize(st));
+    return SPG_OK;
+}
+
+int spg_download_people(spg_handle *h, int32_t n, int32_t *n_persons, double *subset, double *people_xy, double *people_score, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace &ws = h->ws;
+    SPG_D2H(n_persons, ws.n_persons, (size_t)n);
+    SPG_D2H(subset, ws.subset, (size_t)n * ws.capR * (ws.K + 2) * 2);
+    SPG_D2H(people_xy, ws.people_xy, (size_t)n * ws.capR * ws.J * 2);
+    SPG_D2H(people_score, ws.people_score, (size_t)n * ws.capR);
+    SPG_CUDA(h, cudaStreamSynchronize(st));
+    return SPG_OK;
+}
+
+int spg_download_status(spg_handle *h, int32_t n, uint32_t *status, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SPG_D2H(status, h->ws.status, (size_t)n);
+    SPG_CUDA(h, cudaStreamSynchronize(st));
+    return SPG_OK;
+}
+
+}  // extern "C"
