@@ -2,15 +2,26 @@
 //
 // Replaces find_people (/root/reference/evaluate.py:279-498) and the tail of process() (:523-543).
 //
-// The algorithm is a state machine that consumes connections strictly in (limb, acceptance) order, so it
-// is serial per image; throughput comes from the batch (one warp per image, all images concurrent).
-// The `subset` table lives in shared memory in structure-of-arrays form -- id[part][row],
-// score[part][row], total[row], count[row], maxlen[row] -- so that the per-connection scan "which rows
-// hold idA in slot A or idB in slot B" is one conflict-free shared-memory read per lane plus a ballot.
-// np.delete of a merged row (:424) becomes a tombstone bit: row order, which decides which two rows a
-// connection matches (:304-318) and the output order, is unchanged by that.
-// Connections of the current limb are prefetched 32 at a time (one per lane) and broadcast by shuffle,
-// keeping global-memory latency off the serial chain.
+// The reference is a state machine that consumes connections strictly in (limb, acceptance) order.  Two
+// facts make it parallel inside a limb without changing any result:
+//
+//  (1) Ownership invariant.  At any time a peak id sits in at most one live row of `subset`: a new row is
+//      only created when neither end point is in any row (:473), an assignment/replacement only happens
+//      when exactly one row matched (:320), a merge moves ids between two disjoint rows (:403-424).  So the
+//      scan "which rows hold idA in slot A or idB in slot B" (:304-318) returns at most one row per end
+//      point (its third-match branch :314-316 is dead) and can be an O(1) lookup in an owner map
+//      owner[part][peak] -> row.
+//  (2) Independence.  A connection only reads and writes the rows it matched, plus a fresh row when it
+//      matched none.  Connections of one limb have pairwise distinct end points (greedy matching, :265),
+//      so if no row is matched by two connections of the limb they commute; the only order-dependent
+//      quantity, the index of a newly created row, is a prefix count.
+//
+// One warp per image.  Each chunk of <= 32 connections of a limb is classified in parallel (one lane per
+// connection); if every matched row is touched once, all lanes apply their connection simultaneously,
+// otherwise the chunk is replayed sequentially in acceptance order by one lane (rare: contested rows).
+// Both modes run the same single-thread transition function, so they cannot diverge.  np.delete of a
+// merged row (:424) is a tombstone: row order, which decides j1 < j2 in a merge and the output order, is
+// unchanged by that.  `subset` lives in shared memory as structure-of-arrays.
 #pragma once
 
 #include "common.cuh"
@@ -27,12 +38,132 @@ struct AssembleArgs {
 constexpr int kAssembleThreads = 32;
 
 inline size_t assemble_smem_bytes(int K, int capP, int capR) {
-    return (size_t)K * capR * sizeof(double)      // sc
-           + 2 * (size_t)capR * sizeof(double)    // total, maxlen
-           + (size_t)K * capR * sizeof(int)       // id
-           + (size_t)capR * sizeof(int)           // cnt
-           + (size_t)K * capP * sizeof(float)     // peak scores
-           + (size_t)(K + 1) * sizeof(int);       // part offsets
+    size_t b = (size_t)K * capR * sizeof(double)      // sc
+               + 2 * (size_t)capR * sizeof(double)    // total, maxlen
+               + (size_t)K * capR * sizeof(int)       // id
+               + 2 * (size_t)capR * sizeof(int)       // cnt, touch
+               + (size_t)K * capP * sizeof(float)     // peak scores
+               + (size_t)(K + 1) * sizeof(int)        // part offsets
+               + (size_t)K * capP * sizeof(short)     // owner
+               + (size_t)capR;                        // alive
+    return (b + 15) & ~(size_t)15;
+}
+
+struct PersonTable {
+    double *sc, *total, *maxlen;
+    int *id, *cnt, *touch, *off;
+    float *ps;
+    short *owner;
+    unsigned char *alive;
+    int K, capP, capR;
+};
+
+// The reference's per-connection transition (:320-488), executed by ONE thread.  `new_row` is the row index to
+// use if the connection matches nothing.  Returns status flags.
+__device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const AssembleArgs &a, int A, int B, int ia,
+                                                     int jb, double s, double len, int new_row) {
+    const int K = t.K, capP = t.capP, capR = t.capR;
+    const int idA = t.off[A] + ia, idB = t.off[B] + jb;
+    const int ra = t.owner[A * capP + ia], rb = t.owner[B * capP + jb];
+    if (ra < 0 && rb < 0) {  // new person (:473-488)
+        const int j = new_row;
+        for (int c = 0; c < K; c++) {
+            t.id[c * capR + j] = -1;
+            t.sc[c * capR + j] = -1.0;
+        }
+        t.id[A * capR + j] = idA;
+        t.sc[A * capR + j] = s;
+        t.id[B * capR + j] = idB;
+        t.sc[B * capR + j] = s;
+        t.cnt[j] = 2;
+        t.maxlen[j] = len;
+        // builtin sum() of the two end-point scores, then + s (:484)
+        t.total[j] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, (double)t.ps[A * capP + ia]), (double)t.ps[B * capP + jb]), s);
+        t.alive[j] = 1;
+        t.owner[A * capP + ia] = (short)j;
+        t.owner[B * capP + jb] = (short)j;
+        return 0;
+    }
+    if (ra >= 0 && rb >= 0 && ra != rb) {  // two rows (:385-460), j1 < j2 in row order
+        const int j1 = min(ra, rb), j2 = max(ra, rb);
+        bool overlap = false;
+        double m = INFINITY;
+        for (int c = 0; c < K; c++) {
+            const int i1 = t.id[c * capR + j1], i2 = t.id[c * capR + j2];
+            overlap |= (i1 >= 0 && i2 >= 0);
+            if (i1 >= 0) m = fmin(m, t.sc[c * capR + j1]);
+            if (i2 >= 0) m = fmin(m, t.sc[c * capR + j2]);
+        }
+        if (!overlap) {  // disjoint -> merge j2 into j1 (:403-424)
+            const double ml1 = t.maxlen[j1];
+            if (s < __dmul_rn(a.connection_tole, m) || __dmul_rn(a.len_rate, ml1) <= len) return 0;
+            for (int c = 0; c < K; c++) {  // the "+1" trick (:415): absent slots are -1 in both columns
+                const int i2 = t.id[c * capR + j2];
+                t.id[c * capR + j1] = t.id[c * capR + j1] + i2 + 1;
+                t.sc[c * capR + j1] = __dadd_rn(t.sc[c * capR + j1], __dadd_rn(t.sc[c * capR + j2], 1.0));
+                if (i2 >= 0) t.owner[c * capP + (i2 - t.off[c])] = (short)j1;
+            }
+            t.total[j1] = __dadd_rn(__dadd_rn(t.total[j1], t.total[j2]), s);  // :419, :421
+            t.cnt[j1] += t.cnt[j2];
+            t.maxlen[j1] = len > ml1 ? len : ml1;  // keeps j1's own longest limb (:422)
+            t.alive[j2] = 0;                        // np.delete(subset, j2) (:424)
+            return 0;
+        }
+        // overlapping rows (:426-460): only remove_recon > 0 has side effects
+        bool a_in_1 = false;
+        for (int c = 0; c < K; c++) a_in_1 |= (t.id[c * capR + j1] == idA);
+        const int k1 = a_in_1 ? idA : idB, k2 = a_in_1 ? idB : idA;
+        int c1 = -1, c2 = -1, n1 = 0, n2 = 0;
+        for (int c = 0; c < K; c++) {
+            if (t.id[c * capR + j1] == k1) { c1 = c; n1++; }
+            if (t.id[c * capR + j2] == k2) { c2 = c; n2++; }
+        }
+        if (n1 != 1 || n2 != 1 || c1 == c2) return kStAssert;  // the reference would raise (:437-439)
+        const double e1 = t.sc[c1 * capR + j1], e2 = t.sc[c2 * capR + j2];
+        if ((s < e1 && s < e2) || a.remove_recon <= 0) return 0;
+        int small_j = j1, rc = c1;
+        if (e1 > e2) { small_j = j2; rc = c2; }
+        const int rid = t.id[rc * capR + small_j];
+        const int ridx = rid - t.off[rc];
+        t.total[small_j] = __dsub_rn(t.total[small_j], __dadd_rn((double)t.ps[rc * capP + ridx], t.sc[rc * capR + small_j]));
+        t.id[rc * capR + small_j] = -1;
+        t.sc[rc * capR + small_j] = -1.0;
+        t.cnt[small_j] -= 1;
+        t.owner[rc * capP + ridx] = -1;
+        return 0;
+    }
+    // exactly one row (:320-383) -- always slot B of the matched row
+    const int j = ra >= 0 ? ra : rb;
+    const int oldB = t.id[B * capR + j];
+    const double scB = t.sc[B * capR + j];
+    const double ml = t.maxlen[j];
+    const double reach = __dmul_rn(a.len_rate, ml);
+    const double add = __dadd_rn((double)t.ps[B * capP + jb], s);
+    if (oldB == -1 && reach > len) {  // assign (:323-342)
+        t.id[B * capR + j] = idB;
+        t.sc[B * capR + j] = s;
+        t.cnt[j] += 1;
+        t.total[j] = __dadd_rn(t.total[j], add);
+        t.maxlen[j] = len > ml ? len : ml;
+        t.owner[B * capP + jb] = (short)j;
+    } else if (oldB != idB) {
+        if (!(scB >= s) && !(reach <= len)) {  // replace (:346-363)
+            const int oldIdx = oldB >= 0 ? oldB - t.off[B] : 0;
+            const double sub = __dadd_rn((double)t.ps[B * capP + oldIdx], scB);
+            t.total[j] = __dadd_rn(__dsub_rn(t.total[j], sub), add);
+            t.id[B * capR + j] = idB;
+            t.sc[B * capR + j] = s;
+            t.maxlen[j] = len > ml ? len : ml;
+            if (oldB >= 0) t.owner[B * capP + oldIdx] = -1;
+            t.owner[B * capP + jb] = (short)j;
+        }
+    } else if (scB <= s) {  // same B, refresh its score (:368-380)
+        const double sub = __dadd_rn((double)t.ps[B * capP + jb], scB);
+        t.total[j] = __dadd_rn(__dsub_rn(t.total[j], sub), add);
+        t.sc[B * capR + j] = s;
+        t.maxlen[j] = len > ml ? len : ml;
+    }
+    return 0;
 }
 
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -45,180 +176,129 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     const int n = a.image_base + blockIdx.x;
     const int K = ws.K, L = ws.L, capP = ws.capP, capR = ws.capR;
 
-    double *s_sc = reinterpret_cast<double *>(smem_raw);
-    double *s_total = s_sc + (size_t)K * capR;
-    double *s_maxlen = s_total + capR;
-    int *s_id = reinterpret_cast<int *>(s_maxlen + capR);
-    int *s_cnt = s_id + (size_t)K * capR;
-    float *s_ps = reinterpret_cast<float *>(s_cnt + capR);
-    int *s_off = reinterpret_cast<int *>(s_ps + (size_t)K * capP);
+    PersonTable t;
+    t.K = K; t.capP = capP; t.capR = capR;
+    t.sc = reinterpret_cast<double *>(smem_raw);
+    t.total = t.sc + (size_t)K * capR;
+    t.maxlen = t.total + capR;
+    t.id = reinterpret_cast<int *>(t.maxlen + capR);
+    t.cnt = t.id + (size_t)K * capR;
+    t.touch = t.cnt + capR;
+    t.ps = reinterpret_cast<float *>(t.touch + capR);
+    t.off = reinterpret_cast<int *>(t.ps + (size_t)K * capP);
+    t.owner = reinterpret_cast<short *>(t.off + (K + 1));
+    t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
 
     if (lane == 0) {
         int acc = 0;
         for (int c = 0; c < K; c++) {
-            s_off[c] = acc;
+            t.off[c] = acc;
             acc += min(ws.peak_count[(size_t)n * K + c], capP);
         }
-        s_off[K] = acc;
+        t.off[K] = acc;
     }
-    for (int t = lane; t < K * capP; t += 32) s_ps[t] = ws.peak_score[(size_t)n * K * capP + t];
+    for (int i = lane; i < K * capP; i += 32) {
+        t.ps[i] = ws.peak_score[(size_t)n * K * capP + i];
+        t.owner[i] = -1;
+    }
+    for (int i = lane; i < capR; i += 32) {
+        t.touch[i] = 0;
+        t.alive[i] = 0;
+    }
     __syncwarp();
 
-    uint32_t alive[4] = {0, 0, 0, 0};  // tombstone mask, uniform across lanes
     int nrows = 0;
     uint32_t flags = 0;
     bool overflow = false;
 
-    for (int k = 0; k < L && !overflow; k++) {
+    // software prefetch of the next limb's first chunk keeps the L2 latency off the per-limb chain
+    auto load_limb = [&](int k, int &cc, uint32_t &ij, double &s, double &len) {
+        cc = -1; ij = 0; s = 0.0; len = 0.0;
+        if (k >= L) return;
         const size_t slot = (size_t)n * L + k;
-        const int cc = ws.conn_count[slot];
+        cc = ws.conn_count[slot];
+        if (lane < cc) {
+            ij = ws.conn_ij[slot * capP + lane];
+            s = ws.conn_score[slot * capP + lane];
+            len = ws.conn_norm[slot * capP + lane];
+        }
+    };
+    int cc_n; uint32_t ij_n; double s_n, len_n;
+    load_limb(0, cc_n, ij_n, s_n, len_n);
+
+    for (int k = 0; k < L && !overflow; k++) {
+        const int cc = cc_n;
+        uint32_t my_ij = ij_n;
+        double my_s = s_n, my_len = len_n;
+        load_limb(k + 1, cc_n, ij_n, s_n, len_n);
         if (cc < 0) continue;  // special_k (:290)
         const int A = ws.limbs[2 * k], B = ws.limbs[2 * k + 1];
-        const int offA = s_off[A], offB = s_off[B];
+        const size_t slot = (size_t)n * L + k;
         for (int chunk = 0; chunk < cc && !overflow; chunk += 32) {
-            const int mine = chunk + lane;
-            uint32_t my_ij = 0;
-            double my_s = 0.0, my_len = 0.0;
-            if (mine < cc) {
-                my_ij = ws.conn_ij[slot * capP + mine];
-                my_s = ws.conn_score[slot * capP + mine];
-                my_len = ws.conn_norm[slot * capP + mine];
+            if (chunk > 0) {
+                const int mine = chunk + lane;
+                if (mine < cc) {
+                    my_ij = ws.conn_ij[slot * capP + mine];
+                    my_s = ws.conn_score[slot * capP + mine];
+                    my_len = ws.conn_norm[slot * capP + mine];
+                }
             }
             const int in_chunk = min(32, cc - chunk);
-            for (int r = 0; r < in_chunk; r++) {
-                const uint32_t ij = __shfl_sync(0xffffffffu, my_ij, r);
-                const double s = shfl_f64(my_s, r);
-                const double len = shfl_f64(my_len, r);
-                const int ia = (int)(ij >> 16), jb = (int)(ij & 0xffff);
-                const int idA = offA + ia, idB = offB + jb;
-
-                // ---- which (at most two, lowest-index) live rows hold idA in slot A or idB in slot B (:304-318)
-                int found = 0, j1 = -1, j2 = -1;
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    if (w * 32 < nrows && found < 2) {
-                        const int j = w * 32 + lane;
-                        bool hit = false;
-                        if (j < nrows && ((alive[w] >> lane) & 1u))
-                            hit = (s_id[A * capR + j] == idA) || (s_id[B * capR + j] == idB);
-                        uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                        while (mask && found < 2) {
-                            const int b = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            if (found == 0) j1 = w * 32 + b; else j2 = w * 32 + b;
-                            found++;
-                        }
+            const bool active = lane < in_chunk;
+            const int ia = (int)(my_ij >> 16), jb = (int)(my_ij & 0xffff);
+            int ra = -1, rb = -1;
+            if (active) {
+                ra = t.owner[A * capP + ia];
+                rb = t.owner[B * capP + jb];
+                if (ra >= 0) atomicAdd(&t.touch[ra], 1);
+                if (rb >= 0 && rb != ra) atomicAdd(&t.touch[rb], 1);
+            }
+            __syncwarp();
+            const bool contested = active && ((ra >= 0 && t.touch[ra] > 1) || (rb >= 0 && t.touch[rb] > 1));
+            const uint32_t any_contested = __ballot_sync(0xffffffffu, contested);
+            __syncwarp();
+            if (active) {
+                if (ra >= 0) t.touch[ra] = 0;
+                if (rb >= 0) t.touch[rb] = 0;
+            }
+            const uint32_t creates = __ballot_sync(0xffffffffu, active && ra < 0 && rb < 0);
+            if (nrows + __popc(creates) > capR) {
+                flags |= kStRowOverflow;
+                overflow = true;
+                break;
+            }
+            __syncwarp();
+            if (any_contested == 0) {
+                // every matched row is touched by exactly one connection of this chunk: they commute
+                const int my_row = nrows + __popc(creates & ((1u << lane) - 1u));
+                if (active) flags |= apply_connection(t, a, A, B, ia, jb, my_s, my_len, my_row);
+                nrows += __popc(creates);
+            } else {
+                // contested rows: replay the chunk in acceptance order on one lane
+                for (int r = 0; r < in_chunk; r++) {
+                    const uint32_t ij = __shfl_sync(0xffffffffu, my_ij, r);
+                    const double s = shfl_f64(my_s, r);
+                    const double len = shfl_f64(my_len, r);
+                    int made = 0;
+                    if (lane == 0) {
+                        const int cia = (int)(ij >> 16), cjb = (int)(ij & 0xffff);
+                        made = (t.owner[A * capP + cia] < 0 && t.owner[B * capP + cjb] < 0) ? 1 : 0;
+                        if (made && nrows >= capR) made = -1;  // an earlier replacement freed this end point: one more row
+                        else flags |= apply_connection(t, a, A, B, cia, cjb, s, len, nrows);
                     }
-                }
-
-                if (found == 1) {  // :320-383 -- always slot B of the matched row
-                    const int j = j1;
-                    const int oldB = s_id[B * capR + j];
-                    const double scB = s_sc[B * capR + j];
-                    const double ml = s_maxlen[j];
-                    const double reach = __dmul_rn(a.len_rate, ml);
-                    const double add = __dadd_rn((double)s_ps[B * capP + jb], s);
-                    if (oldB == -1 && reach > len) {  // assign (:323-342)
-                        if (lane == 0) {
-                            s_id[B * capR + j] = idB;
-                            s_sc[B * capR + j] = s;
-                            s_cnt[j] += 1;
-                            s_total[j] = __dadd_rn(s_total[j], add);
-                            s_maxlen[j] = len > ml ? len : ml;
-                        }
-                    } else if (oldB != idB) {
-                        if (!(scB >= s) && !(reach <= len)) {  // replace (:346-363)
-                            if (lane == 0) {
-                                const int oldIdx = oldB >= 0 ? oldB - offB : 0;
-                                const double sub = __dadd_rn((double)s_ps[B * capP + oldIdx], scB);
-                                s_total[j] = __dadd_rn(__dsub_rn(s_total[j], sub), add);
-                                s_id[B * capR + j] = idB;
-                                s_sc[B * capR + j] = s;
-                                s_maxlen[j] = len > ml ? len : ml;
-                            }
-                        }
-                    } else if (scB <= s) {  // same B, refresh its score (:368-380)
-                        if (lane == 0) {
-                            const double sub = __dadd_rn((double)s_ps[B * capP + jb], scB);
-                            s_total[j] = __dadd_rn(__dsub_rn(s_total[j], sub), add);
-                            s_sc[B * capR + j] = s;
-                            s_maxlen[j] = len > ml ? len : ml;
-                        }
-                    }
-                    __syncwarp();
-                } else if (found == 2) {  // :385-460
-                    const int id1 = lane < K ? s_id[lane * capR + j1] : -1;
-                    const int id2 = lane < K ? s_id[lane * capR + j2] : -1;
-                    const double sc1 = lane < K ? s_sc[lane * capR + j1] : 0.0;
-                    const double sc2 = lane < K ? s_sc[lane * capR + j2] : 0.0;
-                    const uint32_t both = __ballot_sync(0xffffffffu, id1 >= 0 && id2 >= 0);
-                    if (both == 0) {  // disjoint -> merge j2 into j1 (:403-424)
-                        double m = fmin(id1 >= 0 ? sc1 : INFINITY, id2 >= 0 ? sc2 : INFINITY);
-#pragma unroll
-                        for (int sft = 16; sft > 0; sft >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, sft));
-                        const double ml1 = s_maxlen[j1];
-                        if (!(s < __dmul_rn(a.connection_tole, m) || __dmul_rn(a.len_rate, ml1) <= len)) {
-                            if (lane < K) {  // the "+1" trick (:415): absent slots are -1 in both columns
-                                s_id[lane * capR + j1] = id1 + id2 + 1;
-                                s_sc[lane * capR + j1] = __dadd_rn(sc1, __dadd_rn(sc2, 1.0));
-                            }
-                            if (lane == 0) {
-                                s_total[j1] = __dadd_rn(__dadd_rn(s_total[j1], s_total[j2]), s);  // :419, :421
-                                s_cnt[j1] += s_cnt[j2];
-                                s_maxlen[j1] = len > ml1 ? len : ml1;  // keeps j1's own longest limb (:422)
-                            }
-                            alive[j2 >> 5] &= ~(1u << (j2 & 31));  // np.delete(subset, j2) (:424)
-                        }
-                    } else {  // overlapping rows (:426-460): only remove_recon > 0 has side effects
-                        const uint32_t a_in_1 = __ballot_sync(0xffffffffu, id1 == idA);
-                        const int k1 = a_in_1 ? idA : idB, k2 = a_in_1 ? idB : idA;
-                        const uint32_t m1 = __ballot_sync(0xffffffffu, id1 == k1);
-                        const uint32_t m2 = __ballot_sync(0xffffffffu, id2 == k2);
-                        if (__popc(m1) != 1 || __popc(m2) != 1 || m1 == m2) {
-                            flags |= kStAssert;  // the reference would raise (:437-439)
-                        } else {
-                            const int c1 = __ffs(m1) - 1, c2 = __ffs(m2) - 1;
-                            const double e1 = s_sc[c1 * capR + j1], e2 = s_sc[c2 * capR + j2];
-                            if (!(s < e1 && s < e2) && a.remove_recon > 0) {
-                                int small_j = j1, rc = c1;
-                                if (e1 > e2) { small_j = j2; rc = c2; }
-                                if (lane == 0) {
-                                    const int rid = s_id[rc * capR + small_j];
-                                    const double sub = __dadd_rn((double)s_ps[rc * capP + (rid - s_off[rc])],
-                                                                 s_sc[rc * capR + small_j]);
-                                    s_total[small_j] = __dsub_rn(s_total[small_j], sub);
-                                    s_id[rc * capR + small_j] = -1;
-                                    s_sc[rc * capR + small_j] = -1.0;
-                                    s_cnt[small_j] -= 1;
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                } else {  // new person (:473-488)
-                    if (nrows >= capR) {
+                    made = __shfl_sync(0xffffffffu, made, 0);
+                    if (made < 0) {
                         flags |= kStRowOverflow;
                         overflow = true;
                         break;
                     }
-                    const int j = nrows;
-                    if (lane < K) {
-                        s_id[lane * capR + j] = lane == A ? idA : (lane == B ? idB : -1);
-                        s_sc[lane * capR + j] = (lane == A || lane == B) ? s : -1.0;
-                    }
-                    if (lane == 0) {
-                        s_cnt[j] = 2;
-                        s_maxlen[j] = len;
-                        // builtin sum() of the two end-point scores, then + s (:484)
-                        s_total[j] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, (double)s_ps[A * capP + ia]), (double)s_ps[B * capP + jb]), s);
-                    }
-                    alive[j >> 5] |= 1u << (j & 31);
-                    nrows++;
-                    __syncwarp();
+                    nrows += made;
                 }
             }
+            __syncwarp();
         }
     }
+    flags = __reduce_or_sync(0xffffffffu, flags);
 
     // ---- prune (:491-496) + outputs.  Kept rows keep their relative order.
     const int RS = K + 2, J = ws.J;
@@ -228,36 +308,41 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     const double *g_px = ws.peak_x + (size_t)n * K * capP;
     const double *g_py = ws.peak_y + (size_t)n * K * capP;
     int out = 0;
-    for (int j = 0; j < nrows; j++) {
-        if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
-        const int cnt = s_cnt[j];
-        const double total = s_total[j];
-        if (cnt < a.min_parts || __ddiv_rn(total, (double)cnt) < a.min_mean_score) continue;
-        double *row = g_subset + (size_t)out * RS * 2;
-        if (lane < K) {
-            row[lane * 2 + 0] = (double)s_id[lane * capR + j];
-            row[lane * 2 + 1] = s_sc[lane * capR + j];
+    for (int base = 0; base < nrows; base += 32) {
+        const int j = base + lane;
+        bool keep = false;
+        if (j < nrows && t.alive[j]) {
+            const int cnt = t.cnt[j];
+            keep = !(cnt < a.min_parts || __ddiv_rn(t.total[j], (double)cnt) < a.min_mean_score);
         }
-        if (lane == 0) {
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int o = out + __popc(km & ((1u << lane) - 1u));
+            double *row = g_subset + (size_t)o * RS * 2;
+            for (int c = 0; c < K; c++) {
+                row[c * 2 + 0] = (double)t.id[c * capR + j];
+                row[c * 2 + 1] = t.sc[c * capR + j];
+            }
+            const double total = t.total[j];
             row[K * 2 + 0] = total;
             row[K * 2 + 1] = -1.0;
-            row[(K + 1) * 2 + 0] = (double)cnt;
-            row[(K + 1) * 2 + 1] = s_maxlen[j];
-            g_score[out] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
-        }
-        for (int g = lane; g < J; g += 32) {  // :523-539
-            const int part = ws.out_from_part[g];
-            const int id = s_id[part * capR + j];
-            double x = 0.0, y = 0.0;
-            if (id >= 0) {
-                const int idx = id - s_off[part];
-                x = g_px[part * capP + idx];
-                y = g_py[part * capP + idx];
+            row[(K + 1) * 2 + 0] = (double)t.cnt[j];
+            row[(K + 1) * 2 + 1] = t.maxlen[j];
+            g_score[o] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
+            for (int g = 0; g < J; g++) {                         // :523-539
+                const int part = ws.out_from_part[g];
+                const int id = t.id[part * capR + j];
+                double x = 0.0, y = 0.0;
+                if (id >= 0) {
+                    const int idx = id - t.off[part];
+                    x = g_px[part * capP + idx];
+                    y = g_py[part * capP + idx];
+                }
+                g_xy[((size_t)o * J + g) * 2 + 0] = x;
+                g_xy[((size_t)o * J + g) * 2 + 1] = y;
             }
-            g_xy[((size_t)out * J + g) * 2 + 0] = x;
-            g_xy[((size_t)out * J + g) * 2 + 1] = y;
         }
-        out++;
+        out += __popc(km);
     }
     if (lane == 0) {
         ws.n_persons[n] = out;
