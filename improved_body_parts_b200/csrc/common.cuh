@@ -45,6 +45,7 @@ struct Workspace {
     double *cand_prio, *cand_score;  // [N][L][capC]
     uint32_t *cand_ij;
     int32_t *cand_count;             // [N][L]  -1 = special_k
+    int32_t *surv_count;             // [N][L]  pairs that survived limb_score's screen (diagnostic)
     // connections, acceptance order
     uint32_t *conn_ij;             // [N][L][capP]
     double *conn_score, *conn_norm;

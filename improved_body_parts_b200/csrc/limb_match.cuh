@@ -6,10 +6,14 @@
 //
 // Sequential greedy over a strict total order is the same as repeatedly taking the best remaining
 // candidate whose end points are both free.  One WARP per (image, limb) does exactly that: each lane
-// holds a strided slice of the survivors in registers, every round is a warp arg-max on the key
-// (priority desc, i*nB + j asc) -- the reference's stable-sort order, ties keep (i-major, j-minor)
-// generation order -- and the winner's end points are struck from two 128-bit masks.  Rows come out in
-// acceptance order, which find_people depends on.  No shared memory, no block barrier.
+// holds a strided slice of the survivors in registers as a sortable key
+//     (order-preserving bits of the f64 priority, ~((i << 16) | j))
+// whose lexicographic maximum is the reference's next pick -- priority descending, ties in (i-major,
+// j-minor) generation order, which is what Python's stable sorted(..., reverse=True) yields (:259).
+// A round is three REDUX.MAX warp reductions (hi word, lo word, tie-break word); every lane then strikes
+// its own candidates that share an end point with the winner (two 16-bit compares each), so no "used"
+// masks are needed.  Rows come out in acceptance order, which find_people depends on.  No shared memory,
+// no block barrier.  Limbs with more than 256 survivors take a slower generic path.
 #pragma once
 
 #include "common.cuh"
@@ -22,16 +26,16 @@ struct MatchArgs {
 };
 
 constexpr int kMatchThreads = 128;
-constexpr int kMatchRegCands = 8;  // survivors cached per lane (x32 lanes); beyond that we re-read L2
-
-struct MatchKey {
-    double prio;
-    int p;    // i*nB + j, generation order
-    int idx;  // position in the candidate list, -1 = none
-};
+constexpr int kMatchRegCands = 8;  // survivors cached per lane (x32 lanes)
 
 __device__ __forceinline__ bool key_better(double pa, int ia, double pb, int ib) {
     return pa > pb || (pa == pb && ia < ib);
+}
+
+// order-preserving map f64 -> u64 (larger double <=> larger integer); -0.0 < +0.0 is harmless here
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
 __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) {
@@ -55,78 +59,87 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
     const size_t obase = slot * ws.capP;
     const size_t baseA = ((size_t)n * ws.K + pa) * ws.capP, baseB = ((size_t)n * ws.K + pb) * ws.capP;
 
-    // register cache of this lane's survivors: candidate c = lane + 32*r
-    double r_prio[kMatchRegCands];
-    uint32_t r_ij[kMatchRegCands];
-#pragma unroll
-    for (int r = 0; r < kMatchRegCands; r++) {
-        const int cidx = lane + 32 * r;
-        const bool ok = cidx < nC;
-        r_prio[r] = ok ? ws.cand_prio[cbase + cidx] : 0.0;
-        r_ij[r] = ok ? ws.cand_ij[cbase + cidx] : 0xffffffffu;  // 0xffffffff = dead
-    }
-
-    unsigned long long uA0 = 0, uA1 = 0, uB0 = 0, uB1 = 0;
-    auto used = [&](uint32_t ij) {
-        const int i = ij >> 16, j = ij & 0xffff;
-        const unsigned long long ma = (i < 64 ? uA0 : uA1) >> (i & 63);
-        const unsigned long long mb = (j < 64 ? uB0 : uB1) >> (j & 63);
-        return ((ma | mb) & 1ull) != 0;
+    auto emit = [&](int m, uint32_t ij, int cidx) {  // row [idA, idB, score, i, j, norm] (evaluate.py:267)
+        const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
+        const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
+        const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
+        ws.conn_ij[obase + m] = ij;
+        ws.conn_score[obase + m] = ws.cand_score[cbase + cidx];
+        ws.conn_norm[obase + m] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
     };
 
     int m = 0;
-    while (m < lim) {
-        double bp = 0.0;
-        int bi = 0x7fffffff, bidx = -1;
+    if (nC <= 32 * kMatchRegCands) {
+        // ---- fast path: all survivors live in registers --------------------------------------------
+        unsigned long long r_key[kMatchRegCands];  // ordered priority bits; 0 = dead / absent
+        uint32_t r_tie[kMatchRegCands];            // ~((i << 16) | j): larger = earlier in generation order
 #pragma unroll
         for (int r = 0; r < kMatchRegCands; r++) {
-            const uint32_t ij = r_ij[r];
-            if (ij == 0xffffffffu) continue;
-            if (used(ij)) {
-                r_ij[r] = 0xffffffffu;
-                continue;
-            }
-            const int p = (int)(ij >> 16) * nB + (int)(ij & 0xffff);
-            if (bidx < 0 || key_better(r_prio[r], p, bp, bi)) {
-                bp = r_prio[r];
-                bi = p;
-                bidx = lane + 32 * r;
-            }
+            const int cidx = lane + 32 * r;
+            const bool ok = cidx < nC;
+            r_key[r] = ok ? ordered_bits(ws.cand_prio[cbase + cidx]) : 0ull;
+            r_tie[r] = ok ? ~ws.cand_ij[cbase + cidx] : 0u;
         }
-        for (int cidx = lane + 32 * kMatchRegCands; cidx < nC; cidx += 32) {  // rare: > 256 survivors
-            const uint32_t ij = ws.cand_ij[cbase + cidx];
-            if (used(ij)) continue;
-            const double pr = ws.cand_prio[cbase + cidx];
-            const int p = (int)(ij >> 16) * nB + (int)(ij & 0xffff);
-            if (bidx < 0 || key_better(pr, p, bp, bi)) {
-                bp = pr;
-                bi = p;
-                bidx = cidx;
-            }
-        }
+        while (m < lim) {
+            // lane-local best
+            unsigned long long bk = 0ull;
+            uint32_t bt = 0u;
+            int br = -1;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const double op = __shfl_xor_sync(0xffffffffu, bp, s);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
-            const int oidx = __shfl_xor_sync(0xffffffffu, bidx, s);
-            if (oidx >= 0 && (bidx < 0 || key_better(op, oi, bp, bi))) {
-                bp = op;
-                bi = oi;
-                bidx = oidx;
+            for (int r = 0; r < kMatchRegCands; r++) {
+                const bool better = r_key[r] > bk || (r_key[r] == bk && r_key[r] != 0ull && r_tie[r] > bt);
+                if (better) { bk = r_key[r]; bt = r_tie[r]; br = r; }
             }
+            // warp arg-max on (hi, lo, tie) with three REDUX.MAX
+            const uint32_t hi = (uint32_t)(bk >> 32), lo = (uint32_t)bk;
+            const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+            if (mhi == 0u) break;  // nothing alive anywhere (ordered bits of any real priority have a non-zero hi word)
+            const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+            const bool tied = (hi == mhi) && (lo == mlo);
+            const uint32_t mt = __reduce_max_sync(0xffffffffu, tied ? bt : 0u);
+            const uint32_t wij = ~mt;  // winner's (i << 16) | j
+            if (tied && bt == mt) emit(m, wij, lane + 32 * br);  // exactly one lane: (i, j) pairs are unique
+            // strike everything that shares an end point with the winner (including the winner itself)
+#pragma unroll
+            for (int r = 0; r < kMatchRegCands; r++) {
+                const uint32_t x = ~r_tie[r] ^ wij;
+                if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
+            }
+            m++;
         }
-        if (bidx < 0) break;  // no candidate with both end points free
-        const int i = bi / nB, j = bi - i * nB;
-        if (i < 64) uA0 |= 1ull << i; else uA1 |= 1ull << (i - 64);
-        if (j < 64) uB0 |= 1ull << j; else uB1 |= 1ull << (j - 64);
-        if (lane == 0) {  // row [idA, idB, score, i, j, norm] (evaluate.py:267)
-            const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
-            const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
-            ws.conn_ij[obase + m] = ((uint32_t)i << 16) | (uint32_t)j;
-            ws.conn_score[obase + m] = ws.cand_score[cbase + bidx];
-            ws.conn_norm[obase + m] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    } else {
+        // ---- generic path: re-read the list from L2 every round, 128-bit used masks -------------------
+        unsigned long long uA0 = 0, uA1 = 0, uB0 = 0, uB1 = 0;
+        auto used = [&](uint32_t ij) {
+            const int i = ij >> 16, j = ij & 0xffff;
+            const unsigned long long ma = (i < 64 ? uA0 : uA1) >> (i & 63);
+            const unsigned long long mb = (j < 64 ? uB0 : uB1) >> (j & 63);
+            return ((ma | mb) & 1ull) != 0;
+        };
+        while (m < lim) {
+            double bp = 0.0;
+            int bi = 0x7fffffff, bidx = -1;
+            for (int cidx = lane; cidx < nC; cidx += 32) {
+                const uint32_t ij = ws.cand_ij[cbase + cidx];
+                if (used(ij)) continue;
+                const double pr = ws.cand_prio[cbase + cidx];
+                const int p = (int)(ij >> 16) * nB + (int)(ij & 0xffff);
+                if (bidx < 0 || key_better(pr, p, bp, bi)) { bp = pr; bi = p; bidx = cidx; }
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const double op = __shfl_xor_sync(0xffffffffu, bp, s);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+                const int oidx = __shfl_xor_sync(0xffffffffu, bidx, s);
+                if (oidx >= 0 && (bidx < 0 || key_better(op, oi, bp, bi))) { bp = op; bi = oi; bidx = oidx; }
+            }
+            if (bidx < 0) break;  // no candidate with both end points free
+            const int i = bi / nB, j = bi - i * nB;
+            if (i < 64) uA0 |= 1ull << i; else uA1 |= 1ull << (i - 64);
+            if (j < 64) uB0 |= 1ull << j; else uB1 |= 1ull << (j - 64);
+            if (lane == 0) emit(m, ((uint32_t)i << 16) | (uint32_t)j, bidx);
+            m++;
         }
-        m++;
     }
     if (lane == 0) ws.conn_count[slot] = m;
 }

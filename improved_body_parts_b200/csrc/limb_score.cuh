@@ -5,14 +5,27 @@
 // One CTA per (image, limb).  The limb's body-part plane (H*W elements, one contiguous span) is staged
 // into shared memory by the bulk-copy engine (TMA, SASS UBLKCP) in a few large chunks on one mbarrier,
 // while the threads stage the two end-point peak lists; HBM is read exactly once per plane element and
-// all <= nA*nB*mid_num nearest-neighbour gathers hit shared memory.  Planes that do not fit in shared
-// memory (e.g. 512x512) are sampled through L2 instead (STAGE = false).
+// all nearest-neighbour gathers hit shared memory.  Planes that do not fit in shared memory (e.g.
+// 512x512) are sampled through L2 instead (STAGE = false).
 //
-// One THREAD per candidate pair, not one warp: the reference sums the <= mid_num samples of a pair
-// sequentially (Python sum() over np.float32, evaluate.py:241), and a shuffle-tree reduction would round
-// differently and can flip threshold / ordering decisions downstream.  The warp-level primitive used here
-// is the aggregated append of surviving candidates.  Survivors are written unordered; the matcher orders
-// them by (priority desc, i*nB+j asc), which is the reference's stable-sort order (evaluate.py:259).
+// Two phases keep the kernel on the HBM roofline instead of the issue roofline (nA*nB pairs per limb,
+// ~3 % of which are real limbs):
+//   A. SCREEN, one thread per pair, cheap f32 arithmetic.  A pair can only become a candidate if at
+//      least ceil(connect_ration*m) of its m samples exceed thre2 (:246), i.e. it tolerates at most
+//      maxfail = m - ceil(.) failing samples.  The screen looks at <= 6 interior samples and counts a
+//      failure only when it is CERTAIN: the f32 sample position is farther than 1/64 px from a rounding
+//      boundary (so it rounds to the same pixel as the reference's f64 position) and the map value there
+//      is <= thre2.  More than maxfail certain failures => the reference rejects the pair => drop it.
+//      Anything uncertain (near-boundary sample, sample count m near a rounding boundary, end points close
+//      to the border, coincident end points) survives.  The screen can only drop pairs the reference
+//      drops; it never decides an accept.
+//   B. EXACT, one thread per surviving pair: the reference's arithmetic operation for operation --
+//      f64 np.linspace positions, half-to-even rounding, SEQUENTIAL sum of the samples in the plane's
+//      precision (Python sum() over np.float32, :241; a shuffle-tree reduction would round differently and
+//      can flip threshold / ordering decisions), f32/f64 score and priority exactly as numpy promotes them.
+// Survivors are handed from A to B through a bitmask + prefix sums in shared memory (balanced, ordered,
+// no atomics); candidates are appended with a warp-aggregated shared-memory atomic and written unordered --
+// the matcher orders them by (priority desc, i*nB+j asc), the reference's stable-sort order (:259).
 #pragma once
 
 #include "common.cuh"
@@ -22,17 +35,99 @@ namespace spg {
 struct ScoreArgs {
     const void *paf;
     int64_t img_stride, chan_stride;  // elements
-    int H, W, image_base, mid_num;
+    int H, W, image_base, mid_num, screen;
     double image_extent, thre2, connect_ration;
     Workspace ws;
 };
 
 constexpr int kScoreThreads = 256;
 constexpr uint32_t kBulkChunkBytes = 32768;
+constexpr int kScreenMaxMid = 63;       // maxfail table size
+constexpr float kScreenGuard = 1.0f / 64.0f;
+constexpr int kScreenMaxDim = 2048;     // f32 position error << guard up to this map size
 
 inline size_t score_smem_bytes(size_t plane_bytes, int capP) {
     const size_t plane = (plane_bytes + 127) & ~(size_t)127;
-    return plane + (size_t)capP * (4 * sizeof(double) + 2 * sizeof(float));
+    const size_t peaks = (size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2);
+    const size_t words = ((size_t)capP * capP + 31) / 32;
+    return plane + ((peaks + 15) & ~(size_t)15) + words * (sizeof(uint32_t) + sizeof(uint16_t)) + 16;
+}
+
+struct PairGeom {  // one limb's end-point lists in shared memory
+    const double *ax, *ay, *bx, *by;
+    const float *as, *bs;
+};
+
+// Phase B: the reference's evaluation of one pair (evaluate.py:224-255).  Returns true if it is a candidate.
+template <typename T>
+__device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, int H, int W, const ScoreArgs &a,
+                                                 const PairGeom &g, int i, int j, bool interior, T thre2,
+                                                 double &score, double &prio, bool &bad) {
+    const double ax = g.ax[i], ay = g.ay[i], bx = g.bx[j], by = g.by[j];
+    const double vx = __dsub_rn(bx, ax), vy = __dsub_rn(by, ay);                            // :224
+    const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));        // :225
+    if (norm == 0.0) return false;                                                          // :228-230
+    int m = __double2int_rn(__dadd_rn(norm, 1.0));                                          // :226 round() half-even
+    m = min(m, a.mid_num);
+    // np.linspace(A, B, m): step = delta/(m-1); y_t = t*step + start (two roundings); y_{m-1} = stop
+    const double stepx = m > 1 ? __ddiv_rn(vx, (double)(m - 1)) : 0.0;
+    const double stepy = m > 1 ? __ddiv_rn(vy, (double)(m - 1)) : 0.0;
+    T sum = (T)0;
+    int above = 0;
+    if (interior) {
+        // both end points round to pixels at least 1 px inside the map and samples stay between them:
+        // no index can leave the map, no negative index can wrap
+        double td = 0.0;
+        for (int t = 0; t < m - 1; t++) {
+            const int xi = __double2int_rn(__dadd_rn(__dmul_rn(td, stepx), ax));
+            const int yi = __double2int_rn(__dadd_rn(__dmul_rn(td, stepy), ay));            // :235 nearest neighbour
+            const T v = plane[yi * W + xi];
+            sum = sum + v;  // sequential, in sample order, in the plane's precision (:241)
+            above += v > thre2;
+            td = __dadd_rn(td, 1.0);
+        }
+        const T v = m > 1 ? plane[__double2int_rn(by) * W + __double2int_rn(bx)]
+                          : plane[__double2int_rn(ay) * W + __double2int_rn(ax)];
+        sum = sum + v;
+        above += v > thre2;
+    } else {
+        for (int t = 0; t < m; t++) {
+            double sx, sy;
+            if (t == m - 1 && m > 1) {
+                sx = bx;
+                sy = by;
+            } else {
+                sx = __dadd_rn(__dmul_rn((double)t, stepx), ax);
+                sy = __dadd_rn(__dmul_rn((double)t, stepy), ay);
+            }
+            int yi = __double2int_rn(sy), xi = __double2int_rn(sx);
+            if (yi < 0) yi += H;  // numpy index semantics: negatives wrap once
+            if (xi < 0) xi += W;
+            if (yi < 0 || yi >= H || xi < 0 || xi >= W) {  // the reference would raise IndexError
+                bad = true;
+                return false;
+            }
+            const T v = plane[(size_t)yi * W + xi];
+            sum = sum + v;
+            above += v > thre2;
+        }
+    }
+    // :241 -- `image_width` is the image HEIGHT at the call site (:510)
+    const double prior = __dsub_rn(__ddiv_rn(__dmul_rn(0.5, a.image_extent), norm), 1.0);
+    if (sizeof(T) == 4) {
+        float s = __fdiv_rn((float)sum, (float)m);
+        s = __fadd_rn(s, prior < 0.0 ? __double2float_rn(prior) : 0.0f);  // f32 + weak Python float
+        const float pr = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, s), __fmul_rn(0.25f, g.as[i])), __fmul_rn(0.25f, g.bs[j]));
+        score = (double)s;
+        prio = (double)pr;
+    } else {
+        score = __dadd_rn(__ddiv_rn((double)sum, (double)m), prior < 0.0 ? prior : 0.0);
+        prio = __dadd_rn(__dadd_rn(__dmul_rn(0.5, score), (double)__fmul_rn(0.25f, g.as[i])),
+                         (double)__fmul_rn(0.25f, g.bs[j]));
+    }
+    const bool crit1 = (double)above >= __dmul_rn(a.connect_ration, (double)m);             // :246
+    const bool crit2 = score > 0.0;                                                         // :251
+    return crit1 && crit2;
 }
 
 template <typename T, bool STAGE>
@@ -41,16 +136,18 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     __shared__ uint64_t bar;
     __shared__ int s_count;
     __shared__ uint32_t s_flags;
+    __shared__ int s_total_surv;
+    __shared__ signed char s_maxfail[kScreenMaxMid + 1];
 
     const Workspace &ws = a.ws;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = blockIdx.x % ws.L;
     const int n_local = blockIdx.x / ws.L;
     const int n = a.image_base + n_local;
-    const int H = a.H, W = a.W;
+    const int H = a.H, W = a.W, capP = ws.capP;
     const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
-    const int nA = min(ws.peak_count[(size_t)n * ws.K + pa], ws.capP);
-    const int nB = min(ws.peak_count[(size_t)n * ws.K + pb], ws.capP);
+    const int nA = min(ws.peak_count[(size_t)n * ws.K + pa], capP);
+    const int nB = min(ws.peak_count[(size_t)n * ws.K + pb], capP);
     const size_t slot = (size_t)n * ws.L + k;
     if (nA == 0 || nB == 0) {  // special_k (evaluate.py:272-274)
         if (tid == 0) ws.cand_count[slot] = -1;
@@ -59,14 +156,24 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
 
     const T *gplane = reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride;
     const size_t plane_bytes = (size_t)H * W * sizeof(T);
-    T *splane = reinterpret_cast<T *>(smem_raw);
     unsigned char *after = smem_raw + (STAGE ? ((plane_bytes + 127) & ~(size_t)127) : 0);
     double *s_ax = reinterpret_cast<double *>(after);
-    double *s_ay = s_ax + ws.capP;
-    double *s_bx = s_ay + ws.capP;
-    double *s_by = s_bx + ws.capP;
-    float *s_as = reinterpret_cast<float *>(s_by + ws.capP);
-    float *s_bs = s_as + ws.capP;
+    double *s_ay = s_ax + capP;
+    double *s_bx = s_ay + capP;
+    double *s_by = s_bx + capP;
+    float *s_as = reinterpret_cast<float *>(s_by + capP);
+    float *s_bs = s_as + capP;
+    float *s_fax = s_bs + capP;
+    float *s_fay = s_fax + capP;
+    float *s_fbx = s_fay + capP;
+    float *s_fby = s_fbx + capP;
+    unsigned char *s_ain = reinterpret_cast<unsigned char *>(s_fby + capP);  // end point safely inside the map
+    unsigned char *s_bin = s_ain + capP;
+    const size_t peaks_bytes = ((size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2) + 15) & ~(size_t)15;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(after + peaks_bytes);  // survivor bitmask, bit p = i*nB + j
+    const int npairs = nA * nB;
+    const int nwords = (npairs + 31) >> 5;
+    uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_mask + (((size_t)capP * capP + 31) >> 5));
 
     if (tid == 0) {
         s_count = 0;
@@ -82,79 +189,126 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
         }
     }
     // end-point lists (refined float coordinates + peak scores), overlapped with the plane copy
-    const size_t baseA = ((size_t)n * ws.K + pa) * ws.capP, baseB = ((size_t)n * ws.K + pb) * ws.capP;
+    const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
+    auto inside = [&](double x, double y) {
+        return x >= 1.0 && x <= (double)(W - 2) && y >= 1.0 && y <= (double)(H - 2);
+    };
     for (int i = tid; i < nA; i += kScoreThreads) {
-        s_ax[i] = ws.peak_x[baseA + i];
-        s_ay[i] = ws.peak_y[baseA + i];
+        const double x = ws.peak_x[baseA + i], y = ws.peak_y[baseA + i];
+        s_ax[i] = x; s_ay[i] = y;
+        s_fax[i] = (float)x; s_fay[i] = (float)y;
         s_as[i] = ws.peak_score[baseA + i];
+        s_ain[i] = inside(x, y);
     }
     for (int j = tid; j < nB; j += kScoreThreads) {
-        s_bx[j] = ws.peak_x[baseB + j];
-        s_by[j] = ws.peak_y[baseB + j];
+        const double x = ws.peak_x[baseB + j], y = ws.peak_y[baseB + j];
+        s_bx[j] = x; s_by[j] = y;
+        s_fbx[j] = (float)x; s_fby[j] = (float)y;
         s_bs[j] = ws.peak_score[baseB + j];
+        s_bin[j] = inside(x, y);
+    }
+    const bool screen = a.screen && a.mid_num <= kScreenMaxMid && H <= kScreenMaxDim && W <= kScreenMaxDim;
+    if (tid <= a.mid_num && tid <= kScreenMaxMid) {
+        // fewest samples that must exceed thre2: smallest integer >= connect_ration*m in f64, as :246 compares
+        const double need = __dmul_rn(a.connect_ration, (double)tid);
+        int need_i = (int)need;
+        if ((double)need_i < need) need_i++;
+        s_maxfail[tid] = (signed char)max(min(tid - need_i, 127), -1);
     }
     __syncthreads();
     if (STAGE) mbar_wait(&bar, 0);
-    const T *plane = STAGE ? splane : gplane;
-
+    const T *plane = STAGE ? reinterpret_cast<const T *>(smem_raw) : gplane;
     const T thre2 = (T)a.thre2;  // f32 plane: `> thre2` is an f32 compare against (float)thre2
+
+    // ---------------- phase A: conservative screen ----------------
+    const uint32_t magic = nB > 1 ? (uint32_t)((0x100000000ull + nB - 1) / nB) : 0;  // p / nB == umulhi(p, magic), p < 2^14
+    for (int base = 0; base < npairs; base += kScoreThreads) {
+        const int p = base + tid;
+        bool keep = false;
+        if (p < npairs) {
+            keep = true;
+            if (screen) {
+                const int i = nB > 1 ? (int)__umulhi((uint32_t)p, magic) : p;
+                const int j = p - i * nB;
+                if (s_ain[i] && s_bin[j]) {
+                    const float fax = s_fax[i], fay = s_fay[i];
+                    const float dx = s_fbx[j] - fax, dy = s_fby[j] - fay;
+                    const float n2 = dx * dx + dy * dy;
+                    if (n2 > 1e-6f) {
+                        const float q = sqrtf(n2) + 1.0f;
+                        int m = -1;
+                        if (q >= (float)a.mid_num + 0.51f) {
+                            m = a.mid_num;
+                        } else {
+                            const float r = rintf(q);
+                            if (fabsf(q - r) < 0.49f) m = min((int)r, a.mid_num);  // else: m uncertain -> survive
+                        }
+                        if (m >= 1) {
+                            const int maxfail = s_maxfail[m];
+                            const int lo = m / 6, hi = m - 1 - lo;
+                            const int qn = min(6, hi - lo + 1);
+                            const float inv = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
+                            const float sxf = dx * inv, syf = dy * inv;
+                            const int tstep = qn > 1 ? ((hi - lo) << 8) / (qn - 1) : 0;  // 8.8 fixed point
+                            int fails = 0;
+                            for (int s = 0; s < qn; s++) {
+                                const int t = lo + ((s * tstep) >> 8);
+                                const float x = fax + (float)t * sxf, y = fay + (float)t * syf;
+                                const float rx = rintf(x), ry = rintf(y);
+                                // certain only if >= 1/64 px away from the .5 rounding boundaries
+                                const bool certain = fabsf(x - rx) < 0.5f - kScreenGuard && fabsf(y - ry) < 0.5f - kScreenGuard;
+                                const T v = plane[(int)ry * W + (int)rx];
+                                fails += (certain && !(v > thre2));
+                            }
+                            keep = fails <= maxfail;
+                        }
+                    }
+                }
+            }
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_mask[(base >> 5) + warp] = bits;  // base is a multiple of 256: word = p / 32
+    }
+    __syncthreads();
+    // exclusive prefix of popcounts over the mask words (one warp)
+    if (warp == 0) {
+        int running = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int w = w0 + lane;
+            const int c = w < nwords ? __popc(s_mask[w]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (w < nwords) s_prefix[w] = (uint16_t)(running + incl - c);
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_total_surv = running;
+    }
+    __syncthreads();
+
+    // ---------------- phase B: exact evaluation of the survivors ----------------
+    const int total_surv = s_total_surv;
+    PairGeom g{s_ax, s_ay, s_bx, s_by, s_as, s_bs};
     const size_t out_base = slot * ws.capC;
-    const int npairs = nA * nB;
-    for (int p = tid; p < npairs; p += kScoreThreads) {
-        const int i = p / nB, j = p - i * nB;
-        const double ax = s_ax[i], ay = s_ay[i], bx = s_bx[j], by = s_by[j];
-        const double vx = __dsub_rn(bx, ax), vy = __dsub_rn(by, ay);                           // :224
-        const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));       // :225
-        if (norm == 0.0) continue;                                                             // :228-230
-        int m = __double2int_rn(__dadd_rn(norm, 1.0));                                         // :226 round() half-even
-        m = min(m, a.mid_num);
-        // np.linspace(A, B, m): step = delta/(m-1); y_t = t*step + start (two roundings); y_{m-1} = stop
-        const double stepx = m > 1 ? __ddiv_rn(vx, (double)(m - 1)) : 0.0;
-        const double stepy = m > 1 ? __ddiv_rn(vy, (double)(m - 1)) : 0.0;
-        T sum = (T)0;
-        int above = 0;
-        bool bad = false;
-        for (int t = 0; t < m; t++) {
-            double sx, sy;
-            if (t == m - 1 && m > 1) {
-                sx = bx;
-                sy = by;
-            } else {
-                sx = __dadd_rn(__dmul_rn((double)t, stepx), ax);
-                sy = __dadd_rn(__dmul_rn((double)t, stepy), ay);
-            }
-            int yi = __double2int_rn(sy), xi = __double2int_rn(sx);                            // :235 nearest neighbour
-            if (yi < 0) yi += H;  // numpy index semantics: negatives wrap once
-            if (xi < 0) xi += W;
-            if (yi < 0 || yi >= H || xi < 0 || xi >= W) {  // the reference would raise IndexError
-                bad = true;
-                break;
-            }
-            const T v = plane[(size_t)yi * W + xi];
-            sum = sum + v;  // sequential, in sample order, in the plane's precision (:241)
-            above += v > thre2;
+    for (int sidx = tid; sidx < total_surv; sidx += kScoreThreads) {
+        // largest word w with prefix[w] <= sidx, then the (sidx - prefix[w])-th set bit of it
+        int lo = 0, hi = nwords - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)s_prefix[mid] <= sidx) lo = mid; else hi = mid - 1;
         }
-        if (bad) {
-            atomicOr(&s_flags, kStSampleIndex);
-            continue;
-        }
-        // :241 -- `image_width` is the image HEIGHT at the call site (:510)
-        const double prior = __dsub_rn(__ddiv_rn(__dmul_rn(0.5, a.image_extent), norm), 1.0);
+        const int bit = __fns(s_mask[lo], 0, sidx - (int)s_prefix[lo] + 1);
+        const int p = (lo << 5) + bit;
+        const int i = nB > 1 ? (int)__umulhi((uint32_t)p, magic) : p;
+        const int j = p - i * nB;
         double score, prio;
-        if (sizeof(T) == 4) {
-            float s = __fdiv_rn((float)sum, (float)m);
-            s = __fadd_rn(s, prior < 0.0 ? __double2float_rn(prior) : 0.0f);  // f32 + weak Python float
-            const float pr = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, s), __fmul_rn(0.25f, s_as[i])), __fmul_rn(0.25f, s_bs[j]));
-            score = (double)s;
-            prio = (double)pr;
-        } else {
-            score = __dadd_rn(__ddiv_rn((double)sum, (double)m), prior < 0.0 ? prior : 0.0);
-            prio = __dadd_rn(__dadd_rn(__dmul_rn(0.5, score), (double)__fmul_rn(0.25f, s_as[i])),
-                             (double)__fmul_rn(0.25f, s_bs[j]));
-        }
-        const bool crit1 = (double)above >= __dmul_rn(a.connect_ration, (double)m);            // :246
-        const bool crit2 = score > 0.0;                                                        // :251
-        if (crit1 && crit2) {
+        bool bad = false;
+        const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, j, s_ain[i] && s_bin[j], thre2, score, prio, bad);
+        if (bad) atomicOr(&s_flags, kStSampleIndex);
+        if (ok) {
             const int pos = atomicAdd(&s_count, 1);  // warp-aggregated by ptxas (REDUX + one ATOMS)
             if (pos < ws.capC) {
                 ws.cand_prio[out_base + pos] = prio;
@@ -167,6 +321,7 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     if (tid == 0) {
         const int total = s_count;
         ws.cand_count[slot] = min(total, ws.capC);
+        if (ws.surv_count) ws.surv_count[slot] = total_surv;
         uint32_t f = s_flags;
         if (total > ws.capC) f |= kStCandOverflow;
         if (f) atomicOr(&ws.status[n], f);

@@ -43,7 +43,54 @@ __device__ __forceinline__ bool nms_is_peak(const float *buf, int lo, int H, int
     return true;
 }
 
-__global__ void __launch_bounds__(kNmsThreads) nms_peaks_kernel(NmsArgs a) {
+// refine_centroid (utils/util.py:204-211) for an interior peak, box (2R+1)^2 read from L2.
+// np.mgrid's first grid varies along ROWS and is the one added to x (axes swapped relative to intent; kept).
+// Both sums follow numpy's pairwise order for n = (2R+1)^2 in [9, 81]: eight running accumulators over
+// i = 0 .. n-2 (n-1 is a multiple of 8 for every odd square), combined as ((0+1)+(2+3))+((4+5)+(6+7)), then
+// the last element.  Streaming into the accumulators keeps everything in registers.
+template <int R>
+__device__ __forceinline__ void refine_box(const float *__restrict__ plane, int W, int x, int y, double &rx, double &ry,
+                                           float &sc) {
+    constexpr int D = 2 * R + 1, N = D * D;
+    if (N == 1) {  // radius 0: offsets are 0/b, the mean is the value itself
+        const float b = __ldg(plane + (size_t)y * W + x);
+        const float s32 = 0.0f + b;
+        rx = __dadd_rn((double)x, __ddiv_rn(__dmul_rn((double)b, 0.0), (double)s32));
+        ry = __dadd_rn((double)y, __ddiv_rn(__dmul_rn((double)b, 0.0), (double)s32));
+        sc = __fdiv_rn(s32, 1.0f);
+        return;
+    }
+    float s[8];
+    double ax[8], ay[8];
+    float ts = 0.0f;
+    double tx = 0.0, ty = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int r = i / D - R, q = i % D - R;
+        const float b = __ldg(plane + (size_t)(y + r) * W + (x + q));
+        const double wr = __dmul_rn((double)b, (double)r), wc = __dmul_rn((double)b, (double)q);
+        if (i < 8) {
+            s[i] = b; ax[i] = wr; ay[i] = wc;
+        } else if (i < N - 1) {
+            s[i & 7] = __fadd_rn(s[i & 7], b);
+            ax[i & 7] = __dadd_rn(ax[i & 7], wr);
+            ay[i & 7] = __dadd_rn(ay[i & 7], wc);
+        } else {
+            ts = b; tx = wr; ty = wc;
+        }
+    }
+    const float s32 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3])),
+                                          __fadd_rn(__fadd_rn(s[4], s[5]), __fadd_rn(s[6], s[7]))), ts);
+    const double sx = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(ax[0], ax[1]), __dadd_rn(ax[2], ax[3])),
+                                          __dadd_rn(__dadd_rn(ax[4], ax[5]), __dadd_rn(ax[6], ax[7]))), tx);
+    const double sy = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(ay[0], ay[1]), __dadd_rn(ay[2], ay[3])),
+                                          __dadd_rn(__dadd_rn(ay[4], ay[5]), __dadd_rn(ay[6], ay[7]))), ty);
+    rx = __dadd_rn((double)x, __ddiv_rn(sx, (double)s32));
+    ry = __dadd_rn((double)y, __ddiv_rn(sy, (double)s32));
+    sc = __fdiv_rn(s32, (float)N);  // score_box.mean() stays f32
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
     __shared__ int s_count;
@@ -97,21 +144,36 @@ __global__ void __launch_bounds__(kNmsThreads) nms_peaks_kernel(NmsArgs a) {
         }
         const int y0 = b * br, y1 = min(y0 + br, H);
         if ((W & 3) == 0) {
+            // float4 groups; a group is rejected with one compare when none of its values reaches thre1.
+            // Neighbour rows/columns are CLAMPED to the image: a clamped neighbour is a pixel that is already
+            // inside the clipped 3x3 window (or the pixel itself), so the window max is unchanged.
             const int W4 = W >> 2;
             const int groups = (y1 - y0) * W4;
             for (int g = tid; g < groups; g += kNmsThreads) {
                 const int r = g / W4, xq = g - r * W4;
-                const int y = y0 + r;
-                const float4 v4 = *reinterpret_cast<const float4 *>(buf + (size_t)(y - lo) * W + 4 * xq);
-                const float m = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
+                const int y = y0 + r, x0 = 4 * xq;
+                const float *rc = buf + (size_t)(y - lo) * W;
+                const float4 c4 = *reinterpret_cast<const float4 *>(rc + x0);
+                const float m = fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w));
                 if (!(m >= a.thr)) continue;
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                const float *ru = buf + (size_t)(max(y - 1, 0) - lo) * W;
+                const float *rd = buf + (size_t)(min(y + 1, H - 1) - lo) * W;
+                const float4 u4 = *reinterpret_cast<const float4 *>(ru + x0);
+                const float4 d4 = *reinterpret_cast<const float4 *>(rd + x0);
+                const int xl = max(x0 - 1, 0), xr = min(x0 + 4, W - 1);
+                const float U[6] = {ru[xl], u4.x, u4.y, u4.z, u4.w, ru[xr]};
+                const float C[6] = {rc[xl], c4.x, c4.y, c4.z, c4.w, rc[xr]};
+                const float D[6] = {rd[xl], d4.x, d4.y, d4.z, d4.w, rd[xr]};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int x = 4 * xq + e;
-                    if (nms_is_peak(buf, lo, H, W, y, x, vv[e], a.thr)) {
+                    const float v = C[e + 1];
+                    // keep = (hmax == heat) & (heat >= thre); np.nonzero(heat * keep) drops exact zeros.
+                    // "all neighbours <= v" (not fmax) so that a NaN neighbour vetoes the peak like torch's max-pool
+                    const bool pk = (v >= a.thr) & (v != 0.0f) & (U[e] <= v) & (U[e + 1] <= v) & (U[e + 2] <= v) &
+                                    (C[e] <= v) & (C[e + 2] <= v) & (D[e] <= v) & (D[e + 1] <= v) & (D[e + 2] <= v);
+                    if (pk) {
                         const int pos = atomicAdd(&s_count, 1);
-                        if (pos < ws.capP) s_list[pos] = (uint32_t)(y * W + x);
+                        if (pos < ws.capP) s_list[pos] = (uint32_t)(y * W + x0 + e);
                     }
                 }
             }
@@ -156,25 +218,14 @@ __global__ void __launch_bounds__(kNmsThreads) nms_peaks_kernel(NmsArgs a) {
             sc = plane[(size_t)y * W + x];
             anchor |= 0x80000000u;
         } else {
-            // util.py:204-211.  np.mgrid's first grid varies along ROWS and is the one added to x.
-            float box[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
-            double wr[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
-            double wc[(2 * kMaxRefineRadius + 1) * (2 * kMaxRefineRadius + 1)];
-            int m = 0;
-            for (int r = -R; r <= R; r++)
-                for (int q = -R; q <= R; q++) {
-                    const float bv = __ldg(plane + (size_t)(y + r) * W + (x + q));
-                    box[m] = bv;
-                    wr[m] = __dmul_rn((double)bv, (double)r);
-                    wc[m] = __dmul_rn((double)bv, (double)q);
-                    m++;
-                }
-            const float s32 = pairwise_sum<float>(box, m);
-            const double off_x = __ddiv_rn(pairwise_sum<double>(wr, m), (double)s32);
-            const double off_y = __ddiv_rn(pairwise_sum<double>(wc, m), (double)s32);
-            rx = __dadd_rn((double)x, off_x);
-            ry = __dadd_rn((double)y, off_y);
-            sc = __fdiv_rn(s32, (float)m);  // score_box.mean() stays f32
+            // util.py:204-211
+            switch (R) {
+                case 0: refine_box<0>(plane, W, x, y, rx, ry, sc); break;
+                case 1: refine_box<1>(plane, W, x, y, rx, ry, sc); break;
+                case 2: refine_box<2>(plane, W, x, y, rx, ry, sc); break;
+                case 3: refine_box<3>(plane, W, x, y, rx, ry, sc); break;
+                default: refine_box<4>(plane, W, x, y, rx, ry, sc); break;
+            }
         }
         ws.peak_x[out_base + t] = rx;
         ws.peak_y[out_base + t] = ry;

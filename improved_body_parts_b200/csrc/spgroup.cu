@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,7 @@ struct spg_handle {
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
+    int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
     std::string err;
 };
@@ -159,6 +161,7 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     a.image_extent = extent;
     a.thre2 = p->thre2;
     a.connect_ration = p->connect_ration;
+    a.screen = h->screen;
     a.ws = h->ws;
     return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);
 }
@@ -249,6 +252,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->device = cfg->device;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     DeviceGuard guard(h->device);
 
     const size_t N = cfg->max_batch, K = cfg->n_parts, L = cfg->n_limbs, J = cfg->n_out_joints;
@@ -268,6 +272,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     A(dalloc(h, &ws.cand_score, N * L * cC));
     A(dalloc(h, &ws.cand_ij, N * L * cC));
     A(dalloc(h, &ws.cand_count, N * L));
+    A(dalloc(h, &ws.surv_count, N * L));
     A(dalloc(h, &ws.conn_ij, N * L * cP));
     A(dalloc(h, &ws.conn_score, N * L * cP));
     A(dalloc(h, &ws.conn_norm, N * L * cP));
@@ -315,6 +320,7 @@ int spg_get_device_view(const spg_handle *h, spg_device_view *v) {
     v->peak_count = ws.peak_count;
     v->conn_ij = ws.conn_ij; v->conn_score = ws.conn_score; v->conn_norm = ws.conn_norm; v->conn_count = ws.conn_count;
     v->cand_count = ws.cand_count;
+    v->surv_count = ws.surv_count;
     v->subset = ws.subset; v->n_persons = ws.n_persons; v->people_xy = ws.people_xy; v->people_score = ws.people_score;
     v->status = ws.status;
     return SPG_OK;

@@ -53,7 +53,7 @@ class _DeviceView(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("max_batch", "n_parts", "n_limbs", "n_out_joints", "cap_peaks", "cap_cands",
                                           "cap_rows")] + \
                [(n, C.c_void_p) for n in ("peak_x", "peak_y", "peak_score", "peak_anchor", "peak_count", "conn_ij",
-                                          "conn_score", "conn_norm", "conn_count", "cand_count", "subset",
+                                          "conn_score", "conn_norm", "conn_count", "cand_count", "surv_count", "subset",
                                           "n_persons", "people_xy", "people_score", "status")]
 
 
@@ -392,4 +392,6 @@ class Grouper:
                 "people_xy": view(v.people_xy, (N, cR, J, 2), "<f8"),
                 "people_score": view(v.people_score, (N, cR), "<f8"),
                 "subset": view(v.subset, (N, cR, K + 2, 2), "<f8"),
-                "status": view(v.status, (N,), "<i4")}
+                "status": view(v.status, (N,), "<i4"),
+                "cand_count": view(v.cand_count, (N, self.L), "<i4"),
+                "surv_count": view(v.surv_count, (N, self.L), "<i4")}

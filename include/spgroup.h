@@ -90,6 +90,7 @@ typedef struct spg_device_view {
     const double *conn_score, *conn_norm;
     const int32_t *conn_count;         /* [N][L]; -1 = special_k (evaluate.py:272-274) */
     const int32_t *cand_count;         /* [N][L] candidates that passed both criteria (evaluate.py:252) */
+    const int32_t *surv_count;         /* [N][L] pairs that survived the scoring kernel's conservative screen (diagnostic) */
     /* persons */
     const double *subset;              /* [N][cap_rows][K+2][2] after the prune (evaluate.py:491-496) */
     const int32_t *n_persons;          /* [N] */

@@ -238,3 +238,32 @@ def test_invalid_arguments_fail_loudly(env):
         g.group_device(t.zeros(1, 18, 64, 64, device=env.dev), t.zeros(1, 30, 64, 64, device=env.dev), 64,
                        dict(offset_radius=9))
     g.close()
+
+
+def test_screen_is_conservative_and_effective(env, monkeypatch):
+    """limb_score's f32 screen may only drop pairs the exact evaluation would drop: identical outputs with the
+    screen disabled, survivors >= candidates, and on clean 30-person images it removes most of the nA*nB pairs."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(8080, 16, 128, 128, 30)
+    params = env.skeleton.default_params()
+    hd, pd = t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev)
+    g = env.Grouper(max_batch=16)
+    g.group_device(hd, pd, 128, params)
+    a = g.fetch()
+    v = g.device_tensors()
+    surv, cand = v["surv_count"][:16].cpu().numpy(), v["cand_count"][:16].cpu().numpy()
+    g.close()
+    monkeypatch.setenv("SPG_NO_SCREEN", "1")
+    g = env.Grouper(max_batch=16)
+    g.group_device(hd, pd, 128, params)
+    b = g.fetch()
+    surv_off = g.device_tensors()["surv_count"][:16].cpu().numpy()
+    g.close()
+    for f in ("conn_count", "cand_count", "conn_ij", "conn_score", "conn_norm", "n_persons", "subset", "people_xy"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert (surv >= cand).all()
+    pairs = np.array([[a.peak_count[i, x] * a.peak_count[i, y] for x, y in env.skeleton.LIMBS] for i in range(16)])
+    assert np.array_equal(surv_off, pairs)           # screen off: every pair is evaluated exactly
+    frac = surv.sum() / pairs.sum()
+    print(f"screen keeps {frac:.3f} of {pairs.sum()} pairs; candidates are {cand.sum() / pairs.sum():.3f}")
+    assert frac < 0.5
