@@ -16,12 +16,17 @@
 //      so if no row is matched by two connections of the limb they commute; the only order-dependent
 //      quantity, the index of a newly created row, is a prefix count.
 //
-// One warp per image.  Each chunk of <= 32 connections of a limb is classified in parallel (one lane per
-// connection); if every matched row is touched once, all lanes apply their connection simultaneously,
-// otherwise the chunk is replayed sequentially in acceptance order by one lane (rare: contested rows).
-// Both modes run the same single-thread transition function, so they cannot diverge.  np.delete of a
-// merged row (:424) is a tombstone: row order, which decides j1 < j2 in a merge and the output order, is
-// unchanged by that.  `subset` lives in shared memory as structure-of-arrays.
+// One warp per image, one lane per connection of the current limb (chunks of 32).  Rounds: every pending
+// connection looks up the rows it matches and posts its lane index on them with a shared-memory atomicMin;
+// a connection is ELIGIBLE when it is the lowest-numbered pending connection on every row it matches --
+// then no earlier pending connection can touch (or re-home the end points of) those rows, so applying it now
+// gives exactly the sequential result.  Eligible connections are pairwise row-disjoint and run their
+// transition simultaneously; the rest wait for the next round (cross-person connection pairs (a,b'),(b,a')
+// in crowds need 2-3 rounds, clean limbs need one).  All lanes run the same single-thread transition
+// function the sequential algorithm would.  Because rows are then created out of acceptance order, every
+// row carries its birth stamp (limb, connection index): "row order" -- which decides j1 < j2 in a merge
+// (:396) and the output order -- is birth order, and np.delete of a merged row (:424) is a tombstone.
+// `subset` lives in shared memory as structure-of-arrays.
 #pragma once
 
 #include "common.cuh"
@@ -41,7 +46,7 @@ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
     size_t b = (size_t)K * capR * sizeof(double)      // sc
                + 2 * (size_t)capR * sizeof(double)    // total, maxlen
                + (size_t)K * capR * sizeof(int)       // id
-               + 2 * (size_t)capR * sizeof(int)       // cnt, touch
+               + 3 * (size_t)capR * sizeof(int)       // cnt, touch, birth
                + (size_t)K * capP * sizeof(float)     // peak scores
                + (size_t)(K + 1) * sizeof(int)        // part offsets
                + (size_t)K * capP * sizeof(short)     // owner
@@ -51,7 +56,7 @@ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
 
 struct PersonTable {
     double *sc, *total, *maxlen;
-    int *id, *cnt, *touch, *off;
+    int *id, *cnt, *touch, *birth, *off;
     float *ps;
     short *owner;
     unsigned char *alive;
@@ -59,9 +64,9 @@ struct PersonTable {
 };
 
 // The reference's per-connection transition (:320-488), executed by ONE thread.  `new_row` is the row index to
-// use if the connection matches nothing.  Returns status flags.
+// use if the connection matches nothing, `birth` its stamp.  Returns status flags.
 __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const AssembleArgs &a, int A, int B, int ia,
-                                                     int jb, double s, double len, int new_row) {
+                                                     int jb, double s, double len, int new_row, int birth) {
     const int K = t.K, capP = t.capP, capR = t.capR;
     const int idA = t.off[A] + ia, idB = t.off[B] + jb;
     const int ra = t.owner[A * capP + ia], rb = t.owner[B * capP + jb];
@@ -80,12 +85,14 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
         // builtin sum() of the two end-point scores, then + s (:484)
         t.total[j] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, (double)t.ps[A * capP + ia]), (double)t.ps[B * capP + jb]), s);
         t.alive[j] = 1;
+        t.birth[j] = birth;
         t.owner[A * capP + ia] = (short)j;
         t.owner[B * capP + jb] = (short)j;
         return 0;
     }
-    if (ra >= 0 && rb >= 0 && ra != rb) {  // two rows (:385-460), j1 < j2 in row order
-        const int j1 = min(ra, rb), j2 = max(ra, rb);
+    if (ra >= 0 && rb >= 0 && ra != rb) {  // two rows (:385-460), j1 before j2 in row (= birth) order
+        const bool a_first = t.birth[ra] < t.birth[rb];
+        const int j1 = a_first ? ra : rb, j2 = a_first ? rb : ra;
         bool overlap = false;
         double m = INFINITY;
         for (int c = 0; c < K; c++) {
@@ -184,7 +191,8 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     t.id = reinterpret_cast<int *>(t.maxlen + capR);
     t.cnt = t.id + (size_t)K * capR;
     t.touch = t.cnt + capR;
-    t.ps = reinterpret_cast<float *>(t.touch + capR);
+    t.birth = t.touch + capR;
+    t.ps = reinterpret_cast<float *>(t.birth + capR);
     t.off = reinterpret_cast<int *>(t.ps + (size_t)K * capP);
     t.owner = reinterpret_cast<short *>(t.off + (K + 1));
     t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         t.owner[i] = -1;
     }
     for (int i = lane; i < capR; i += 32) {
-        t.touch[i] = 0;
+        t.touch[i] = 0x7fffffff;
         t.alive[i] = 0;
     }
     __syncwarp();
@@ -244,58 +252,39 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
                 }
             }
             const int in_chunk = min(32, cc - chunk);
-            const bool active = lane < in_chunk;
             const int ia = (int)(my_ij >> 16), jb = (int)(my_ij & 0xffff);
-            int ra = -1, rb = -1;
-            if (active) {
-                ra = t.owner[A * capP + ia];
-                rb = t.owner[B * capP + jb];
-                if (ra >= 0) atomicAdd(&t.touch[ra], 1);
-                if (rb >= 0 && rb != ra) atomicAdd(&t.touch[rb], 1);
-            }
-            __syncwarp();
-            const bool contested = active && ((ra >= 0 && t.touch[ra] > 1) || (rb >= 0 && t.touch[rb] > 1));
-            const uint32_t any_contested = __ballot_sync(0xffffffffu, contested);
-            __syncwarp();
-            if (active) {
-                if (ra >= 0) t.touch[ra] = 0;
-                if (rb >= 0) t.touch[rb] = 0;
-            }
-            const uint32_t creates = __ballot_sync(0xffffffffu, active && ra < 0 && rb < 0);
-            if (nrows + __popc(creates) > capR) {
-                flags |= kStRowOverflow;
-                overflow = true;
-                break;
-            }
-            __syncwarp();
-            if (any_contested == 0) {
-                // every matched row is touched by exactly one connection of this chunk: they commute
-                const int my_row = nrows + __popc(creates & ((1u << lane) - 1u));
-                if (active) flags |= apply_connection(t, a, A, B, ia, jb, my_s, my_len, my_row);
-                nrows += __popc(creates);
-            } else {
-                // contested rows: replay the chunk in acceptance order on one lane
-                for (int r = 0; r < in_chunk; r++) {
-                    const uint32_t ij = __shfl_sync(0xffffffffu, my_ij, r);
-                    const double s = shfl_f64(my_s, r);
-                    const double len = shfl_f64(my_len, r);
-                    int made = 0;
-                    if (lane == 0) {
-                        const int cia = (int)(ij >> 16), cjb = (int)(ij & 0xffff);
-                        made = (t.owner[A * capP + cia] < 0 && t.owner[B * capP + cjb] < 0) ? 1 : 0;
-                        if (made && nrows >= capR) made = -1;  // an earlier replacement freed this end point: one more row
-                        else flags |= apply_connection(t, a, A, B, cia, cjb, s, len, nrows);
-                    }
-                    made = __shfl_sync(0xffffffffu, made, 0);
-                    if (made < 0) {
-                        flags |= kStRowOverflow;
-                        overflow = true;
-                        break;
-                    }
-                    nrows += made;
+            const int birth = (k << 8) | (chunk + lane);
+            uint32_t pending = in_chunk == 32 ? 0xffffffffu : ((1u << in_chunk) - 1u);
+            while (pending) {
+                const bool mine = (pending >> lane) & 1u;
+                int ra = -1, rb = -1;
+                if (mine) {
+                    ra = t.owner[A * capP + ia];
+                    rb = t.owner[B * capP + jb];
+                    if (ra >= 0) atomicMin(&t.touch[ra], lane);
+                    if (rb >= 0 && rb != ra) atomicMin(&t.touch[rb], lane);
                 }
+                __syncwarp();
+                // lowest pending toucher of every row it matches (the lowest pending lane always qualifies)
+                const bool eligible = mine && (ra < 0 || t.touch[ra] == lane) && (rb < 0 || t.touch[rb] == lane);
+                const uint32_t emask = __ballot_sync(0xffffffffu, eligible);
+                if (mine) {
+                    if (ra >= 0) t.touch[ra] = 0x7fffffff;
+                    if (rb >= 0) t.touch[rb] = 0x7fffffff;
+                }
+                const uint32_t creates = __ballot_sync(0xffffffffu, eligible && ra < 0 && rb < 0);
+                if (nrows + __popc(creates) > capR) {
+                    flags |= kStRowOverflow;
+                    overflow = true;
+                    break;
+                }
+                __syncwarp();
+                if (eligible)
+                    flags |= apply_connection(t, a, A, B, ia, jb, my_s, my_len, nrows + __popc(creates & ((1u << lane) - 1u)), birth);
+                nrows += __popc(creates);
+                pending &= ~emask;
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
@@ -307,42 +296,46 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     double *g_score = ws.people_score + (size_t)n * capR;
     const double *g_px = ws.peak_x + (size_t)n * K * capP;
     const double *g_py = ws.peak_y + (size_t)n * K * capP;
-    int out = 0;
-    for (int base = 0; base < nrows; base += 32) {
-        const int j = base + lane;
+    // keep flags first (reusing `touch`), then each kept row's output position = number of kept rows born earlier
+    for (int j = lane; j < nrows; j += 32) {
         bool keep = false;
-        if (j < nrows && t.alive[j]) {
+        if (t.alive[j]) {
             const int cnt = t.cnt[j];
             keep = !(cnt < a.min_parts || __ddiv_rn(t.total[j], (double)cnt) < a.min_mean_score);
         }
-        const uint32_t km = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int o = out + __popc(km & ((1u << lane) - 1u));
-            double *row = g_subset + (size_t)o * RS * 2;
-            for (int c = 0; c < K; c++) {
-                row[c * 2 + 0] = (double)t.id[c * capR + j];
-                row[c * 2 + 1] = t.sc[c * capR + j];
-            }
-            const double total = t.total[j];
-            row[K * 2 + 0] = total;
-            row[K * 2 + 1] = -1.0;
-            row[(K + 1) * 2 + 0] = (double)t.cnt[j];
-            row[(K + 1) * 2 + 1] = t.maxlen[j];
-            g_score[o] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
-            for (int g = 0; g < J; g++) {                         // :523-539
-                const int part = ws.out_from_part[g];
-                const int id = t.id[part * capR + j];
-                double x = 0.0, y = 0.0;
-                if (id >= 0) {
-                    const int idx = id - t.off[part];
-                    x = g_px[part * capP + idx];
-                    y = g_py[part * capP + idx];
-                }
-                g_xy[((size_t)o * J + g) * 2 + 0] = x;
-                g_xy[((size_t)o * J + g) * 2 + 1] = y;
-            }
+        t.touch[j] = keep ? 1 : 0;
+    }
+    __syncwarp();
+    int out = 0;
+    for (int j = 0; j < nrows; j++) out += t.touch[j];
+    for (int j = lane; j < nrows; j += 32) {
+        if (!t.touch[j]) continue;
+        const int mine = t.birth[j];
+        int o = 0;
+        for (int u = 0; u < nrows; u++) o += (t.touch[u] && t.birth[u] < mine);
+        double *row = g_subset + (size_t)o * RS * 2;
+        for (int c = 0; c < K; c++) {
+            row[c * 2 + 0] = (double)t.id[c * capR + j];
+            row[c * 2 + 1] = t.sc[c * capR + j];
         }
-        out += __popc(km);
+        const double total = t.total[j];
+        row[K * 2 + 0] = total;
+        row[K * 2 + 1] = -1.0;
+        row[(K + 1) * 2 + 0] = (double)t.cnt[j];
+        row[(K + 1) * 2 + 1] = t.maxlen[j];
+        g_score[o] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
+        for (int g = 0; g < J; g++) {                         // :523-539
+            const int part = ws.out_from_part[g];
+            const int id = t.id[part * capR + j];
+            double x = 0.0, y = 0.0;
+            if (id >= 0) {
+                const int idx = id - t.off[part];
+                x = g_px[part * capP + idx];
+                y = g_py[part * capP + idx];
+            }
+            g_xy[((size_t)o * J + g) * 2 + 0] = x;
+            g_xy[((size_t)o * J + g) * 2 + 1] = y;
+        }
     }
     if (lane == 0) {
         ws.n_persons[n] = out;

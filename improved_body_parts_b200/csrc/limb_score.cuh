@@ -12,10 +12,10 @@
 // ~3 % of which are real limbs):
 //   A. SCREEN, one thread per pair, cheap f32 arithmetic.  A pair can only become a candidate if at
 //      least ceil(connect_ration*m) of its m samples exceed thre2 (:246), i.e. it tolerates at most
-//      maxfail = m - ceil(.) failing samples.  The screen looks at <= 6 interior samples and counts a
-//      failure only when it is CERTAIN: the f32 sample position is farther than 1/64 px from a rounding
-//      boundary (so it rounds to the same pixel as the reference's f64 position) and the map value there
-//      is <= thre2.  More than maxfail certain failures => the reference rejects the pair => drop it.
+//      maxfail = m - ceil(.) failing samples.  The screen looks at <= 10 interior samples (positions in
+//      1/64-px fixed point from one FFMA) and counts a failure only when it is CERTAIN: the position is
+//      at least 1.5/64 px away from a rounding boundary (so it rounds to the same pixel as the reference's
+//      f64 position) and the map value there is <= thre2.  More than maxfail certain failures => the reference rejects the pair => drop it.
 //      Anything uncertain (near-boundary sample, sample count m near a rounding boundary, end points close
 //      to the border, coincident end points) survives.  The screen can only drop pairs the reference
 //      drops; it never decides an accept.
@@ -42,20 +42,23 @@ struct ScoreArgs {
 
 constexpr int kScoreThreads = 256;
 constexpr uint32_t kBulkChunkBytes = 32768;
-constexpr int kScreenMaxMid = 63;       // maxfail table size
-constexpr float kScreenGuard = 1.0f / 64.0f;
-constexpr int kScreenMaxDim = 2048;     // f32 position error << guard up to this map size
+constexpr int kScreenMaxMid = 63;       // per-m tables (maxfail, sample positions, reciprocals)
+constexpr int kScreenSamples = 10;      // interior samples looked at per pair
+constexpr int kScreenMaxDim = 2048;     // f32 error of a 1/64-px position stays << 1 unit up to this map size
 
 inline size_t score_smem_bytes(size_t plane_bytes, int capP) {
     const size_t plane = (plane_bytes + 127) & ~(size_t)127;
     const size_t peaks = (size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2);
     const size_t words = ((size_t)capP * capP + 31) / 32;
-    return plane + ((peaks + 15) & ~(size_t)15) + words * (sizeof(uint32_t) + sizeof(uint16_t)) + 16;
+    const size_t tables = (size_t)(kScreenMaxMid + 1) * (sizeof(double) + (kScreenSamples + 1) * sizeof(float) + 2);
+    return plane + ((peaks + 15) & ~(size_t)15) + ((tables + 15) & ~(size_t)15) +
+           words * (sizeof(uint32_t) + sizeof(uint16_t)) + 16;
 }
 
 struct PairGeom {  // one limb's end-point lists in shared memory
     const double *ax, *ay, *bx, *by;
     const float *as, *bs;
+    const double *rcp;  // rcp[d] = RN(1/d), d = 1 .. mid_num-1
 };
 
 // Phase B: the reference's evaluation of one pair (evaluate.py:224-255).  Returns true if it is a candidate.
@@ -65,13 +68,31 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
                                                  double &score, double &prio, bool &bad) {
     const double ax = g.ax[i], ay = g.ay[i], bx = g.bx[j], by = g.by[j];
     const double vx = __dsub_rn(bx, ax), vy = __dsub_rn(by, ay);                            // :224
-    const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));        // :225
-    if (norm == 0.0) return false;                                                          // :228-230
-    int m = __double2int_rn(__dadd_rn(norm, 1.0));                                          // :226 round() half-even
-    m = min(m, a.mid_num);
-    // np.linspace(A, B, m): step = delta/(m-1); y_t = t*step + start (two roundings); y_{m-1} = stop
-    const double stepx = m > 1 ? __ddiv_rn(vx, (double)(m - 1)) : 0.0;
-    const double stepy = m > 1 ? __ddiv_rn(vy, (double)(m - 1)) : 0.0;
+    const double n2 = __dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy));
+    if (n2 == 0.0) return false;                             // norm == 0 (:228-230); sqrt(x) == 0 iff x == 0
+    // norm = sqrt(n2) (:225) is only materialised when a decision needs it:
+    //  - m = min(round(norm + 1), mid_num) (:226): n2 >= mid_num^2 implies norm >= mid_num, hence m = mid_num;
+    //  - the distance prior (:241) is negative iff norm > 0.5*extent (correctly rounded division is monotone
+    //    and 1 - 2^-53 is representable), which cannot happen while n2 <= (0.5*extent)^2 * (1 - 1e-9).
+    const double half = __dmul_rn(0.5, a.image_extent);
+    const double Md = (double)a.mid_num;
+    double norm = 0.0;
+    int m = a.mid_num;
+    const bool need_norm = n2 < __dmul_rn(Md, Md) || n2 > __dmul_rn(__dmul_rn(half, half), 1.0 - 1e-9);
+    if (need_norm) {
+        norm = __dsqrt_rn(n2);
+        m = min(__double2int_rn(__dadd_rn(norm, 1.0)), a.mid_num);                           // round() half-even
+    }
+    // np.linspace(A, B, m): step = delta/(m-1); y_t = t*step + start (two roundings); y_{m-1} = stop.
+    // delta/(m-1) by Markstein's correction: with y = RN(1/d), q0 = RN(delta*y), r = RN(delta - q0*d) (exact, FMA),
+    // RN(q0 + r*y) is the correctly rounded quotient (tests/test_numerics.py checks it against exact rationals).
+    double stepx = 0.0, stepy = 0.0;
+    if (m > 1) {
+        const double dd = (double)(m - 1), y = g.rcp[m - 1];
+        const double qx = __dmul_rn(vx, y), qy = __dmul_rn(vy, y);
+        stepx = __fma_rn(__fma_rn(-qx, dd, vx), y, qx);
+        stepy = __fma_rn(__fma_rn(-qy, dd, vy), y, qy);
+    }
     T sum = (T)0;
     int above = 0;
     if (interior) {
@@ -113,7 +134,8 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
         }
     }
     // :241 -- `image_width` is the image HEIGHT at the call site (:510)
-    const double prior = __dsub_rn(__ddiv_rn(__dmul_rn(0.5, a.image_extent), norm), 1.0);
+    double prior = 0.0;  // only its value when negative matters: min(prior, 0)
+    if (need_norm && norm > half) prior = __dsub_rn(__ddiv_rn(half, norm), 1.0);
     if (sizeof(T) == 4) {
         float s = __fdiv_rn((float)sum, (float)m);
         s = __fadd_rn(s, prior < 0.0 ? __double2float_rn(prior) : 0.0f);  // f32 + weak Python float
@@ -137,7 +159,6 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     __shared__ int s_count;
     __shared__ uint32_t s_flags;
     __shared__ int s_total_surv;
-    __shared__ signed char s_maxfail[kScreenMaxMid + 1];
 
     const Workspace &ws = a.ws;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,7 +191,14 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     unsigned char *s_ain = reinterpret_cast<unsigned char *>(s_fby + capP);  // end point safely inside the map
     unsigned char *s_bin = s_ain + capP;
     const size_t peaks_bytes = ((size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2) + 15) & ~(size_t)15;
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(after + peaks_bytes);  // survivor bitmask, bit p = i*nB + j
+    // per-m tables: reciprocals (phase B), screen sample positions, 64/(m-1), #samples, maxfail
+    const size_t tables_bytes = ((size_t)(kScreenMaxMid + 1) * (sizeof(double) + (kScreenSamples + 1) * sizeof(float) + 2) + 15) & ~(size_t)15;
+    double *s_rcp = reinterpret_cast<double *>(after + peaks_bytes);
+    float *s_ts = reinterpret_cast<float *>(s_rcp + (kScreenMaxMid + 1));          // [m][kScreenSamples]
+    float *s_inv64 = s_ts + (size_t)(kScreenMaxMid + 1) * kScreenSamples;           // [m]
+    signed char *s_maxfail = reinterpret_cast<signed char *>(s_inv64 + (kScreenMaxMid + 1));
+    unsigned char *s_qn = reinterpret_cast<unsigned char *>(s_maxfail + (kScreenMaxMid + 1));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(after + peaks_bytes + tables_bytes);  // survivor bitmask, bit p = i*nB + j
     const int npairs = nA * nB;
     const int nwords = (npairs + 31) >> 5;
     uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_mask + (((size_t)capP * capP + 31) >> 5));
@@ -196,24 +224,33 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     for (int i = tid; i < nA; i += kScoreThreads) {
         const double x = ws.peak_x[baseA + i], y = ws.peak_y[baseA + i];
         s_ax[i] = x; s_ay[i] = y;
-        s_fax[i] = (float)x; s_fay[i] = (float)y;
+        s_fax[i] = (float)(x * 64.0); s_fay[i] = (float)(y * 64.0);  // 1/64-px units for the screen
         s_as[i] = ws.peak_score[baseA + i];
         s_ain[i] = inside(x, y);
     }
     for (int j = tid; j < nB; j += kScoreThreads) {
         const double x = ws.peak_x[baseB + j], y = ws.peak_y[baseB + j];
         s_bx[j] = x; s_by[j] = y;
-        s_fbx[j] = (float)x; s_fby[j] = (float)y;
+        s_fbx[j] = (float)(x * 64.0); s_fby[j] = (float)(y * 64.0);
         s_bs[j] = ws.peak_score[baseB + j];
         s_bin[j] = inside(x, y);
     }
     const bool screen = a.screen && a.mid_num <= kScreenMaxMid && H <= kScreenMaxDim && W <= kScreenMaxDim;
     if (tid <= a.mid_num && tid <= kScreenMaxMid) {
+        const int m = tid;
         // fewest samples that must exceed thre2: smallest integer >= connect_ration*m in f64, as :246 compares
-        const double need = __dmul_rn(a.connect_ration, (double)tid);
+        const double need = __dmul_rn(a.connect_ration, (double)m);
         int need_i = (int)need;
         if ((double)need_i < need) need_i++;
-        s_maxfail[tid] = (signed char)max(min(tid - need_i, 127), -1);
+        s_maxfail[m] = (signed char)max(min(m - need_i, 127), -1);
+        s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
+        s_inv64[m] = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
+        // screen positions: up to kScreenSamples sample indices spread over the interior [m/8, m-1-m/8]
+        const int lo = m / 8, hi = m - 1 - lo;
+        const int qn = max(0, min(kScreenSamples, hi - lo + 1));
+        s_qn[m] = (unsigned char)qn;
+        for (int q = 0; q < kScreenSamples; q++)
+            s_ts[m * kScreenSamples + q] = (float)(qn > 1 ? lo + (q * (hi - lo)) / (qn - 1) : lo);
     }
     __syncthreads();
     if (STAGE) mbar_wait(&bar, 0);
@@ -231,9 +268,9 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
                 const int i = nB > 1 ? (int)__umulhi((uint32_t)p, magic) : p;
                 const int j = p - i * nB;
                 if (s_ain[i] && s_bin[j]) {
-                    const float fax = s_fax[i], fay = s_fay[i];
-                    const float dx = s_fbx[j] - fax, dy = s_fby[j] - fay;
-                    const float n2 = dx * dx + dy * dy;
+                    const float ax64 = s_fax[i], ay64 = s_fay[i];
+                    const float dx64 = s_fbx[j] - ax64, dy64 = s_fby[j] - ay64;
+                    const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
                     if (n2 > 1e-6f) {
                         const float q = sqrtf(n2) + 1.0f;
                         int m = -1;
@@ -245,20 +282,20 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
                         }
                         if (m >= 1) {
                             const int maxfail = s_maxfail[m];
-                            const int lo = m / 6, hi = m - 1 - lo;
-                            const int qn = min(6, hi - lo + 1);
-                            const float inv = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
-                            const float sxf = dx * inv, syf = dy * inv;
-                            const int tstep = qn > 1 ? ((hi - lo) << 8) / (qn - 1) : 0;  // 8.8 fixed point
+                            const int qn = s_qn[m];
+                            const float inv = s_inv64[m];
+                            const float sx64 = dx64 * inv, sy64 = dy64 * inv;
+                            const float *ts = s_ts + m * kScreenSamples;
                             int fails = 0;
-                            for (int s = 0; s < qn; s++) {
-                                const int t = lo + ((s * tstep) >> 8);
-                                const float x = fax + (float)t * sxf, y = fay + (float)t * syf;
-                                const float rx = rintf(x), ry = rintf(y);
-                                // certain only if >= 1/64 px away from the .5 rounding boundaries
-                                const bool certain = fabsf(x - rx) < 0.5f - kScreenGuard && fabsf(y - ry) < 0.5f - kScreenGuard;
-                                const T v = plane[(int)ry * W + (int)rx];
-                                fails += (certain && !(v > thre2));
+                            for (int q2 = 0; q2 < qn; q2++) {
+                                const float tf = ts[q2];
+                                // position in 1/64 px, off from the reference's f64 position by < 0.51 units
+                                const int xs = __float2int_rn(__fmaf_rn(tf, sx64, ax64));
+                                const int ys = __float2int_rn(__fmaf_rn(tf, sy64, ay64));
+                                // rounding boundaries sit at 32 (mod 64); within {31,32,33} the pixel is uncertain
+                                const unsigned cx = (unsigned)(xs + 33) & 63u, cy = (unsigned)(ys + 33) & 63u;
+                                const T v = plane[((ys + 32) >> 6) * W + ((xs + 32) >> 6)];
+                                fails += (min(cx, cy) > 2u) && !(v > thre2);
                             }
                             keep = fails <= maxfail;
                         }
@@ -291,7 +328,7 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
 
     // ---------------- phase B: exact evaluation of the survivors ----------------
     const int total_surv = s_total_surv;
-    PairGeom g{s_ax, s_ay, s_bx, s_by, s_as, s_bs};
+    PairGeom g{s_ax, s_ay, s_bx, s_by, s_as, s_bs, s_rcp};
     const size_t out_base = slot * ws.capC;
     for (int sidx = tid; sidx < total_surv; sidx += kScoreThreads) {
         // largest word w with prefix[w] <= sidx, then the (sidx - prefix[w])-th set bit of it
