@@ -46,7 +46,7 @@ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
     size_t b = (size_t)K * capR * sizeof(double)      // sc
                + 2 * (size_t)capR * sizeof(double)    // total, maxlen
                + (size_t)K * capR * sizeof(int)       // id
-               + 3 * (size_t)capR * sizeof(int)       // cnt, touch, birth
+               + 4 * (size_t)capR * sizeof(int)       // cnt, touch, birth, mask
                + (size_t)K * capP * sizeof(float)     // peak scores
                + (size_t)(K + 1) * sizeof(int)        // part offsets
                + (size_t)K * capP * sizeof(short)     // owner
@@ -57,6 +57,7 @@ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
 struct PersonTable {
     double *sc, *total, *maxlen;
     int *id, *cnt, *touch, *birth, *off;
+    uint32_t *mask;  // bit c set <=> slot c of the row holds a peak; id/sc of unset slots are the reference's -1 / -1.0
     float *ps;
     short *owner;
     unsigned char *alive;
@@ -67,15 +68,12 @@ struct PersonTable {
 // use if the connection matches nothing, `birth` its stamp.  Returns status flags.
 __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const AssembleArgs &a, int A, int B, int ia,
                                                      int jb, double s, double len, int new_row, int birth) {
-    const int K = t.K, capP = t.capP, capR = t.capR;
+    const int capP = t.capP, capR = t.capR;
     const int idA = t.off[A] + ia, idB = t.off[B] + jb;
     const int ra = t.owner[A * capP + ia], rb = t.owner[B * capP + jb];
     if (ra < 0 && rb < 0) {  // new person (:473-488)
         const int j = new_row;
-        for (int c = 0; c < K; c++) {
-            t.id[c * capR + j] = -1;
-            t.sc[c * capR + j] = -1.0;
-        }
+        t.mask[j] = (1u << A) | (1u << B);
         t.id[A * capR + j] = idA;
         t.sc[A * capR + j] = s;
         t.id[B * capR + j] = idB;
@@ -93,23 +91,23 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
     if (ra >= 0 && rb >= 0 && ra != rb) {  // two rows (:385-460), j1 before j2 in row (= birth) order
         const bool a_first = t.birth[ra] < t.birth[rb];
         const int j1 = a_first ? ra : rb, j2 = a_first ? rb : ra;
-        bool overlap = false;
-        double m = INFINITY;
-        for (int c = 0; c < K; c++) {
-            const int i1 = t.id[c * capR + j1], i2 = t.id[c * capR + j2];
-            overlap |= (i1 >= 0 && i2 >= 0);
-            if (i1 >= 0) m = fmin(m, t.sc[c * capR + j1]);
-            if (i2 >= 0) m = fmin(m, t.sc[c * capR + j2]);
-        }
-        if (!overlap) {  // disjoint -> merge j2 into j1 (:403-424)
+        const uint32_t m1 = t.mask[j1], m2 = t.mask[j2];
+        if ((m1 & m2) == 0u) {  // disjoint -> merge j2 into j1 (:403-424)
+            double m = INFINITY;  // min over the connection scores present in either row (:405-407)
+            for (uint32_t b = m1; b; b &= b - 1) m = fmin(m, t.sc[(__ffs(b) - 1) * capR + j1]);
+            for (uint32_t b = m2; b; b &= b - 1) m = fmin(m, t.sc[(__ffs(b) - 1) * capR + j2]);
             const double ml1 = t.maxlen[j1];
             if (s < __dmul_rn(a.connection_tole, m) || __dmul_rn(a.len_rate, ml1) <= len) return 0;
-            for (int c = 0; c < K; c++) {  // the "+1" trick (:415): absent slots are -1 in both columns
+            // the "+1" trick (:415) on both columns.  Slots absent from j2 add (-1 + 1) = 0 to j1: unchanged.
+            // Slots present in j2 are absent from j1 (disjoint): id -1 + (id2 + 1), score -1.0 + (sc2 + 1.0).
+            for (uint32_t b = m2; b; b &= b - 1) {
+                const int c = __ffs(b) - 1;
                 const int i2 = t.id[c * capR + j2];
-                t.id[c * capR + j1] = t.id[c * capR + j1] + i2 + 1;
-                t.sc[c * capR + j1] = __dadd_rn(t.sc[c * capR + j1], __dadd_rn(t.sc[c * capR + j2], 1.0));
-                if (i2 >= 0) t.owner[c * capP + (i2 - t.off[c])] = (short)j1;
+                t.id[c * capR + j1] = i2;
+                t.sc[c * capR + j1] = __dadd_rn(-1.0, __dadd_rn(t.sc[c * capR + j2], 1.0));
+                t.owner[c * capP + (i2 - t.off[c])] = (short)j1;
             }
+            t.mask[j1] = m1 | m2;
             t.total[j1] = __dadd_rn(__dadd_rn(t.total[j1], t.total[j2]), s);  // :419, :421
             t.cnt[j1] += t.cnt[j2];
             t.maxlen[j1] = len > ml1 ? len : ml1;  // keeps j1's own longest limb (:422)
@@ -117,36 +115,32 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
             return 0;
         }
         // overlapping rows (:426-460): only remove_recon > 0 has side effects
-        bool a_in_1 = false;
-        for (int c = 0; c < K; c++) a_in_1 |= (t.id[c * capR + j1] == idA);
-        const int k1 = a_in_1 ? idA : idB, k2 = a_in_1 ? idB : idA;
-        int c1 = -1, c2 = -1, n1 = 0, n2 = 0;
-        for (int c = 0; c < K; c++) {
-            if (t.id[c * capR + j1] == k1) { c1 = c; n1++; }
-            if (t.id[c * capR + j2] == k2) { c2 = c; n2++; }
-        }
-        if (n1 != 1 || n2 != 1 || c1 == c2) return kStAssert;  // the reference would raise (:437-439)
+        if (a.remove_recon <= 0) return 0;  // (the lookups below cannot fail: a peak id sits in exactly one slot of one row)
+        const bool a_in_1 = (ra == j1);     // idA is in j1 iff j1 is the row that owns it
+        const int c1 = a_in_1 ? A : B, c2 = a_in_1 ? B : A;
         const double e1 = t.sc[c1 * capR + j1], e2 = t.sc[c2 * capR + j2];
-        if ((s < e1 && s < e2) || a.remove_recon <= 0) return 0;
+        if (s < e1 && s < e2) return 0;
         int small_j = j1, rc = c1;
         if (e1 > e2) { small_j = j2; rc = c2; }
         const int rid = t.id[rc * capR + small_j];
         const int ridx = rid - t.off[rc];
         t.total[small_j] = __dsub_rn(t.total[small_j], __dadd_rn((double)t.ps[rc * capP + ridx], t.sc[rc * capR + small_j]));
-        t.id[rc * capR + small_j] = -1;
-        t.sc[rc * capR + small_j] = -1.0;
+        t.mask[small_j] &= ~(1u << rc);
         t.cnt[small_j] -= 1;
         t.owner[rc * capP + ridx] = -1;
         return 0;
     }
     // exactly one row (:320-383) -- always slot B of the matched row
     const int j = ra >= 0 ? ra : rb;
-    const int oldB = t.id[B * capR + j];
-    const double scB = t.sc[B * capR + j];
+    const uint32_t mj = t.mask[j];
+    const bool hasB = (mj >> B) & 1u;
+    const int oldB = hasB ? t.id[B * capR + j] : -1;
+    const double scB = hasB ? t.sc[B * capR + j] : -1.0;
     const double ml = t.maxlen[j];
     const double reach = __dmul_rn(a.len_rate, ml);
     const double add = __dadd_rn((double)t.ps[B * capP + jb], s);
-    if (oldB == -1 && reach > len) {  // assign (:323-342)
+    if (!hasB && reach > len) {  // assign (:323-342)
+        t.mask[j] = mj | (1u << B);
         t.id[B * capR + j] = idB;
         t.sc[B * capR + j] = s;
         t.cnt[j] += 1;
@@ -154,14 +148,14 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
         t.maxlen[j] = len > ml ? len : ml;
         t.owner[B * capP + jb] = (short)j;
     } else if (oldB != idB) {
-        if (!(scB >= s) && !(reach <= len)) {  // replace (:346-363)
-            const int oldIdx = oldB >= 0 ? oldB - t.off[B] : 0;
+        if (hasB && !(scB >= s) && !(reach <= len)) {  // replace (:346-363); an empty slot only gets here when too long
+            const int oldIdx = oldB - t.off[B];
             const double sub = __dadd_rn((double)t.ps[B * capP + oldIdx], scB);
             t.total[j] = __dadd_rn(__dsub_rn(t.total[j], sub), add);
             t.id[B * capR + j] = idB;
             t.sc[B * capR + j] = s;
             t.maxlen[j] = len > ml ? len : ml;
-            if (oldB >= 0) t.owner[B * capP + oldIdx] = -1;
+            t.owner[B * capP + oldIdx] = -1;
             t.owner[B * capP + jb] = (short)j;
         }
     } else if (scB <= s) {  // same B, refresh its score (:368-380)
@@ -192,7 +186,8 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     t.cnt = t.id + (size_t)K * capR;
     t.touch = t.cnt + capR;
     t.birth = t.touch + capR;
-    t.ps = reinterpret_cast<float *>(t.birth + capR);
+    t.mask = reinterpret_cast<uint32_t *>(t.birth + capR);
+    t.ps = reinterpret_cast<float *>(t.mask + capR);
     t.off = reinterpret_cast<int *>(t.ps + (size_t)K * capP);
     t.owner = reinterpret_cast<short *>(t.off + (K + 1));
     t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
@@ -314,9 +309,11 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         int o = 0;
         for (int u = 0; u < nrows; u++) o += (t.touch[u] && t.birth[u] < mine);
         double *row = g_subset + (size_t)o * RS * 2;
+        const uint32_t mj = t.mask[j];
         for (int c = 0; c < K; c++) {
-            row[c * 2 + 0] = (double)t.id[c * capR + j];
-            row[c * 2 + 1] = t.sc[c * capR + j];
+            const bool has = (mj >> c) & 1u;
+            row[c * 2 + 0] = has ? (double)t.id[c * capR + j] : -1.0;
+            row[c * 2 + 1] = has ? t.sc[c * capR + j] : -1.0;
         }
         const double total = t.total[j];
         row[K * 2 + 0] = total;
@@ -326,7 +323,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         g_score[o] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
         for (int g = 0; g < J; g++) {                         // :523-539
             const int part = ws.out_from_part[g];
-            const int id = t.id[part * capR + j];
+            const int id = ((mj >> part) & 1u) ? t.id[part * capR + j] : -1;
             double x = 0.0, y = 0.0;
             if (id >= 0) {
                 const int idx = id - t.off[part];

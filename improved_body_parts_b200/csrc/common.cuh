@@ -34,8 +34,8 @@ struct Params {
 // Device workspace of one handle (all arrays [max_batch][...]).
 struct Workspace {
     int K, L, J, capP, capC, capR, max_batch;
-    const int32_t *limbs;          // [L][2]
-    const int32_t *out_from_part;  // [J]
+    int16_t limbs[kMaxLimbs * 2];       // [L][2]; lives in the kernel parameter (constant) bank
+    int16_t out_from_part[kMaxOutJoints];  // [J]
     // peaks
     double *peak_x, *peak_y;       // [N][K][capP]
     float *peak_score;
@@ -44,6 +44,7 @@ struct Workspace {
     // candidates (unordered; the matcher orders them by (priority desc, i*nB+j asc))
     double *cand_prio, *cand_score;  // [N][L][capC]
     uint32_t *cand_ij;
+    unsigned long long *cand_key;    // f32 planes only: (order-preserving bits of the f32 priority << 32) | ~((i << 16) | j)
     int32_t *cand_count;             // [N][L]  -1 = special_k
     int32_t *surv_count;             // [N][L]  pairs that survived limb_score's screen (diagnostic)
     // connections, acceptance order

@@ -7,12 +7,13 @@
 // Sequential greedy over a strict total order is the same as repeatedly taking the best remaining
 // candidate whose end points are both free.  One WARP per (image, limb) does exactly that: each lane
 // holds a strided slice of the survivors in registers as a sortable key
-//     (order-preserving bits of the f64 priority, ~((i << 16) | j))
+//     (order-preserving bits of the priority, ~((i << 16) | j))
 // whose lexicographic maximum is the reference's next pick -- priority descending, ties in (i-major,
 // j-minor) generation order, which is what Python's stable sorted(..., reverse=True) yields (:259).
-// A round is three REDUX.MAX warp reductions (hi word, lo word, tie-break word); every lane then strikes
-// its own candidates that share an end point with the winner (two 16-bit compares each), so no "used"
-// masks are needed.  Rows come out in acceptance order, which find_people depends on.  No shared memory,
+// For f32 planes the priority is an f32 value and the whole key is ONE 64-bit word written by the scoring
+// kernel: a round is a lane-local max, two REDUX.MAX warp reductions (hi word, then lo word among the
+// ties), and a strike of every candidate sharing an end point with the winner (two 16-bit compares each;
+// no "used" masks).  f64 planes use a three-word key (f64 priority + tie-break) the same way.  Rows come out in acceptance order, which find_people depends on.  No shared memory,
 // no block barrier.  Limbs with more than 256 survivors take a slower generic path.
 #pragma once
 
@@ -21,7 +22,7 @@
 namespace spg {
 
 struct MatchArgs {
-    int n_images, image_base;
+    int n_images, image_base, keys_valid;
     Workspace ws;
 };
 
@@ -69,8 +70,44 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
     };
 
     int m = 0;
-    if (nC <= 32 * kMatchRegCands) {
-        // ---- fast path: all survivors live in registers --------------------------------------------
+    const int nslots = (nC + 31) >> 5;
+    if (a.keys_valid && nC <= 32 * kMatchRegCands) {
+        // ---- fast path, f32 planes: one 64-bit key per survivor, all in registers -----------------------
+        unsigned long long r_key[kMatchRegCands];  // 0 = dead / absent
+#pragma unroll
+        for (int r = 0; r < kMatchRegCands; r++) {
+            const int cidx = lane + 32 * r;
+            r_key[r] = (r < nslots && cidx < nC) ? ws.cand_key[cbase + cidx] : 0ull;
+        }
+        while (m < lim) {
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int r = 0; r < kMatchRegCands; r++)
+                if (r < nslots) best = max(best, r_key[r]);
+            const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+            const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+            if (mhi == 0u) break;  // nothing alive (a real priority never has an all-zero hi word)
+            const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+            const uint32_t wij = ~mlo;  // winner's (i << 16) | j; (i, j) pairs are unique, so exactly one lane owns it
+            if (hi == mhi && lo == mlo) {
+                int wr = 0;
+#pragma unroll
+                for (int r = 1; r < kMatchRegCands; r++)
+                    if (r_key[r] == best) wr = r;
+                emit(m, wij, lane + 32 * wr);
+            }
+            // strike everything that shares an end point with the winner (including the winner itself)
+#pragma unroll
+            for (int r = 0; r < kMatchRegCands; r++) {
+                if (r < nslots) {
+                    const uint32_t x = ~(uint32_t)r_key[r] ^ wij;
+                    if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
+                }
+            }
+            m++;
+        }
+    } else if (nC <= 32 * kMatchRegCands) {
+        // ---- register path, f64 planes: (ordered f64 priority, tie-break) -------------------------------
         unsigned long long r_key[kMatchRegCands];  // ordered priority bits; 0 = dead / absent
         uint32_t r_tie[kMatchRegCands];            // ~((i << 16) | j): larger = earlier in generation order
 #pragma unroll
@@ -81,7 +118,6 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
             r_tie[r] = ok ? ~ws.cand_ij[cbase + cidx] : 0u;
         }
         while (m < lim) {
-            // lane-local best
             unsigned long long bk = 0ull;
             uint32_t bt = 0u;
             int br = -1;
@@ -90,16 +126,14 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
                 const bool better = r_key[r] > bk || (r_key[r] == bk && r_key[r] != 0ull && r_tie[r] > bt);
                 if (better) { bk = r_key[r]; bt = r_tie[r]; br = r; }
             }
-            // warp arg-max on (hi, lo, tie) with three REDUX.MAX
             const uint32_t hi = (uint32_t)(bk >> 32), lo = (uint32_t)bk;
             const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-            if (mhi == 0u) break;  // nothing alive anywhere (ordered bits of any real priority have a non-zero hi word)
+            if (mhi == 0u) break;
             const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
             const bool tied = (hi == mhi) && (lo == mlo);
             const uint32_t mt = __reduce_max_sync(0xffffffffu, tied ? bt : 0u);
-            const uint32_t wij = ~mt;  // winner's (i << 16) | j
-            if (tied && bt == mt) emit(m, wij, lane + 32 * br);  // exactly one lane: (i, j) pairs are unique
-            // strike everything that shares an end point with the winner (including the winner itself)
+            const uint32_t wij = ~mt;
+            if (tied && bt == mt) emit(m, wij, lane + 32 * br);
 #pragma unroll
             for (int r = 0; r < kMatchRegCands; r++) {
                 const uint32_t x = ~r_tie[r] ^ wij;

@@ -40,7 +40,7 @@ struct ScoreArgs {
     Workspace ws;
 };
 
-constexpr int kScoreThreads = 256;
+constexpr int kScoreThreads = 512;
 constexpr uint32_t kBulkChunkBytes = 32768;
 constexpr int kScreenMaxMid = 63;       // per-m tables (maxfail, sample positions, reciprocals)
 constexpr int kScreenSamples = 10;      // interior samples looked at per pair
@@ -153,7 +153,7 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
 }
 
 template <typename T, bool STAGE>
-__global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ int s_count;
@@ -166,17 +166,34 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     const int n_local = blockIdx.x / ws.L;
     const int n = a.image_base + n_local;
     const int H = a.H, W = a.W, capP = ws.capP;
+    // Start the plane copy before anything that depends on a global load: it is the longest latency of the CTA.
+    const T *gplane = reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride;
+    const size_t plane_bytes = (size_t)H * W * sizeof(T);
+    if (tid == 0) {
+        s_count = 0;
+        s_flags = 0;
+        if (STAGE) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&bar, (uint32_t)plane_bytes);
+            for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
+                const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
+                bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char *>(gplane) + off, bytes, &bar);
+            }
+        }
+    }
     const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
     const int nA = min(ws.peak_count[(size_t)n * ws.K + pa], capP);
     const int nB = min(ws.peak_count[(size_t)n * ws.K + pb], capP);
     const size_t slot = (size_t)n * ws.L + k;
     if (nA == 0 || nB == 0) {  // special_k (evaluate.py:272-274)
-        if (tid == 0) ws.cand_count[slot] = -1;
+        if (tid == 0) {
+            ws.cand_count[slot] = -1;
+            if (STAGE) mbar_wait(&bar, 0);  // the copy must land before the CTA (and its shared memory) goes away
+        }
         return;
     }
 
-    const T *gplane = reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride;
-    const size_t plane_bytes = (size_t)H * W * sizeof(T);
     unsigned char *after = smem_raw + (STAGE ? ((plane_bytes + 127) & ~(size_t)127) : 0);
     double *s_ax = reinterpret_cast<double *>(after);
     double *s_ay = s_ax + capP;
@@ -203,19 +220,6 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
     const int nwords = (npairs + 31) >> 5;
     uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_mask + (((size_t)capP * capP + 31) >> 5));
 
-    if (tid == 0) {
-        s_count = 0;
-        s_flags = 0;
-        if (STAGE) {
-            mbar_init(&bar, 1);
-            fence_mbar_init();
-            mbar_expect_tx(&bar, (uint32_t)plane_bytes);
-            for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
-                const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
-                bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char *>(gplane) + off, bytes, &bar);
-            }
-        }
-    }
     // end-point lists (refined float coordinates + peak scores), overlapped with the plane copy
     const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
     auto inside = [&](double x, double y) {
@@ -350,7 +354,13 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(ScoreArgs a) 
             if (pos < ws.capC) {
                 ws.cand_prio[out_base + pos] = prio;
                 ws.cand_score[out_base + pos] = score;
-                ws.cand_ij[out_base + pos] = ((uint32_t)i << 16) | (uint32_t)j;
+                const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)j;
+                ws.cand_ij[out_base + pos] = ij;
+                if (sizeof(T) == 4) {  // the priority is an f32 value: 32 order-preserving bits + the tie-break fit one word
+                    const uint32_t b = __float_as_uint((float)prio);
+                    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                    ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                }
             }
         }
     }

@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
             // inside the clipped 3x3 window (or the pixel itself), so the window max is unchanged.
             const int W4 = W >> 2;
             const int groups = (y1 - y0) * W4;
-            for (int g = tid; g < groups; g += kNmsThreads) {
-                const int r = g / W4, xq = g - r * W4;
+            // (row, quad) of this thread's first group, then advanced by kNmsThreads groups without dividing
+            int r = tid / W4, xq = tid - r * W4;
+            const int dr = kNmsThreads / W4, dq = kNmsThreads - dr * W4;
+            for (int g = tid; g < groups; g += kNmsThreads, r += dr, xq += dq) {
+                if (xq >= W4) { xq -= W4; r++; }
                 const int y = y0 + r, x0 = 4 * xq;
                 const float *rc = buf + (size_t)(y - lo) * W;
                 const float4 c4 = *reinterpret_cast<const float4 *>(rc + x0);

@@ -36,14 +36,13 @@ struct spg_handle {
     size_t smem_optin = 0;
     Workspace ws{};
     std::vector<void *> allocs;
-    int32_t *d_limbs = nullptr;
-    int32_t *d_out_from_part = nullptr;
     // staging for spg_group_host
     void *in_heat = nullptr, *in_paf = nullptr;
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
     int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
+    int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
     std::string err;
 };
@@ -163,6 +162,7 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     a.connect_ration = p->connect_ration;
     a.screen = h->screen;
     a.ws = h->ws;
+    h->cand_dtype = dtype;
     return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);
 }
 
@@ -171,6 +171,7 @@ int launch_match(spg_handle *h, int base, int n, cudaStream_t st) {
     MatchArgs a{};
     a.n_images = n;
     a.image_base = base;
+    a.keys_valid = h->cand_dtype == SPG_F32;
     a.ws = h->ws;
     const int warps = n * h->ws.L;
     const int blocks = (warps * 32 + kMatchThreads - 1) / kMatchThreads;
@@ -261,8 +262,6 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     ws.K = (int)K; ws.L = (int)L; ws.J = (int)J; ws.capP = (int)cP; ws.capC = (int)cC; ws.capR = (int)cR; ws.max_batch = (int)N;
     int rc = SPG_OK;
     auto A = [&](int r) { if (rc == SPG_OK) rc = r; };
-    A(dalloc(h, &h->d_limbs, L * 2));
-    A(dalloc(h, &h->d_out_from_part, J));
     A(dalloc(h, &ws.peak_x, N * K * cP));
     A(dalloc(h, &ws.peak_y, N * K * cP));
     A(dalloc(h, &ws.peak_score, N * K * cP));
@@ -271,6 +270,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     A(dalloc(h, &ws.cand_prio, N * L * cC));
     A(dalloc(h, &ws.cand_score, N * L * cC));
     A(dalloc(h, &ws.cand_ij, N * L * cC));
+    A(dalloc(h, &ws.cand_key, N * L * cC));
     A(dalloc(h, &ws.cand_count, N * L));
     A(dalloc(h, &ws.surv_count, N * L));
     A(dalloc(h, &ws.conn_ij, N * L * cP));
@@ -282,8 +282,8 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     A(dalloc(h, &ws.people_xy, N * cR * std::max<size_t>(J, 1) * 2));
     A(dalloc(h, &ws.people_score, N * cR));
     A(dalloc(h, &ws.status, N));
-    if (rc == SPG_OK && cudaMemcpy(h->d_limbs, cfg->limbs, sizeof(int32_t) * L * 2, cudaMemcpyHostToDevice) != cudaSuccess) rc = SPG_E_CUDA;
-    if (rc == SPG_OK && J && cudaMemcpy(h->d_out_from_part, cfg->out_from_part, sizeof(int32_t) * J, cudaMemcpyHostToDevice) != cudaSuccess) rc = SPG_E_CUDA;
+    for (size_t i = 0; i < L * 2; i++) ws.limbs[i] = (int16_t)cfg->limbs[i];
+    for (size_t g = 0; g < J; g++) ws.out_from_part[g] = (int16_t)cfg->out_from_part[g];
     if (rc == SPG_OK && cudaMemset(ws.status, 0, sizeof(uint32_t) * N) != cudaSuccess) rc = SPG_E_CUDA;
     if (rc == SPG_OK && cudaMemset(ws.peak_count, 0, sizeof(int32_t) * N * K) != cudaSuccess) rc = SPG_E_CUDA;
     for (int s = 0; s < 2 && rc == SPG_OK; s++)
@@ -293,8 +293,6 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
         spg_destroy(h);
         return rc;
     }
-    ws.limbs = h->d_limbs;
-    ws.out_from_part = h->d_out_from_part;
     *out = h;
     return SPG_OK;
 }
