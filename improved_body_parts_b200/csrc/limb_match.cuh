@@ -39,6 +39,49 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// Greedy rounds over <= 32*NS survivors held in registers (f32 planes: one-word keys).  Specialised on the
+// number of register slots so that limbs with few survivors do not pay for eight.  The accepted row's (i, j)
+// and score are stored by the lane that owns the winner; limb lengths are filled in afterwards in parallel.
+template <int NS>
+__device__ __forceinline__ int match_rounds_keys(const Workspace &ws, size_t cbase, size_t obase, int nC, int lim, int lane) {
+    unsigned long long key[NS];  // 0 = dead / absent
+    double sc[NS];
+#pragma unroll
+    for (int r = 0; r < NS; r++) {
+        const int cidx = lane + 32 * r;
+        const bool ok = cidx < nC;
+        key[r] = ok ? ws.cand_key[cbase + cidx] : 0ull;
+        sc[r] = ok ? ws.cand_score[cbase + cidx] : 0.0;
+    }
+    int m = 0;
+    while (m < lim) {
+        unsigned long long best = key[0];
+#pragma unroll
+        for (int r = 1; r < NS; r++) best = max(best, key[r]);
+        const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+        const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+        if (mhi == 0u) break;  // nothing alive (a real priority never has an all-zero hi word)
+        const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        const uint32_t wij = ~mlo;  // winner's (i << 16) | j; (i, j) pairs are unique, so exactly one lane owns it
+        if (hi == mhi && lo == mlo) {
+            double wsc = sc[0];
+#pragma unroll
+            for (int r = 1; r < NS; r++)
+                if (key[r] == best) wsc = sc[r];
+            ws.conn_ij[obase + m] = wij;      // row [idA, idB, score, i, j, norm] (evaluate.py:267)
+            ws.conn_score[obase + m] = wsc;
+        }
+        // strike everything that shares an end point with the winner (including the winner itself)
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            const uint32_t x = ~(uint32_t)key[r] ^ wij;
+            if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) key[r] = 0ull;
+        }
+        m++;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) {
     const Workspace &ws = a.ws;
     const int lane = threadIdx.x & 31;
@@ -73,38 +116,24 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
     const int nslots = (nC + 31) >> 5;
     if (a.keys_valid && nC <= 32 * kMatchRegCands) {
         // ---- fast path, f32 planes: one 64-bit key per survivor, all in registers -----------------------
-        unsigned long long r_key[kMatchRegCands];  // 0 = dead / absent
-#pragma unroll
-        for (int r = 0; r < kMatchRegCands; r++) {
-            const int cidx = lane + 32 * r;
-            r_key[r] = (r < nslots && cidx < nC) ? ws.cand_key[cbase + cidx] : 0ull;
+        switch (nslots) {
+            case 0: break;
+            case 1: m = match_rounds_keys<1>(ws, cbase, obase, nC, lim, lane); break;
+            case 2: m = match_rounds_keys<2>(ws, cbase, obase, nC, lim, lane); break;
+            case 3: m = match_rounds_keys<3>(ws, cbase, obase, nC, lim, lane); break;
+            case 4: m = match_rounds_keys<4>(ws, cbase, obase, nC, lim, lane); break;
+            case 5: m = match_rounds_keys<5>(ws, cbase, obase, nC, lim, lane); break;
+            case 6: m = match_rounds_keys<6>(ws, cbase, obase, nC, lim, lane); break;
+            case 7: m = match_rounds_keys<7>(ws, cbase, obase, nC, lim, lane); break;
+            default: m = match_rounds_keys<8>(ws, cbase, obase, nC, lim, lane); break;
         }
-        while (m < lim) {
-            unsigned long long best = 0ull;
-#pragma unroll
-            for (int r = 0; r < kMatchRegCands; r++)
-                if (r < nslots) best = max(best, r_key[r]);
-            const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-            const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-            if (mhi == 0u) break;  // nothing alive (a real priority never has an all-zero hi word)
-            const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-            const uint32_t wij = ~mlo;  // winner's (i << 16) | j; (i, j) pairs are unique, so exactly one lane owns it
-            if (hi == mhi && lo == mlo) {
-                int wr = 0;
-#pragma unroll
-                for (int r = 1; r < kMatchRegCands; r++)
-                    if (r_key[r] == best) wr = r;
-                emit(m, wij, lane + 32 * wr);
-            }
-            // strike everything that shares an end point with the winner (including the winner itself)
-#pragma unroll
-            for (int r = 0; r < kMatchRegCands; r++) {
-                if (r < nslots) {
-                    const uint32_t x = ~(uint32_t)r_key[r] ^ wij;
-                    if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
-                }
-            }
-            m++;
+        __syncwarp();  // the rows were written by different lanes of this warp
+        for (int c = lane; c < m; c += 32) {  // limb lengths (the reference's `norm`, :225) in parallel
+            const uint32_t ij = ws.conn_ij[obase + c];
+            const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
+            const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
+            const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
+            ws.conn_norm[obase + c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
         }
     } else if (nC <= 32 * kMatchRegCands) {
         // ---- register path, f64 planes: (ordered f64 priority, tie-break) -------------------------------

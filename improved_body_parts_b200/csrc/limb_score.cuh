@@ -225,36 +225,42 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     auto inside = [&](double x, double y) {
         return x >= 1.0 && x <= (double)(W - 2) && y >= 1.0 && y <= (double)(H - 2);
     };
-    for (int i = tid; i < nA; i += kScoreThreads) {
-        const double x = ws.peak_x[baseA + i], y = ws.peak_y[baseA + i];
-        s_ax[i] = x; s_ay[i] = y;
-        s_fax[i] = (float)(x * 64.0); s_fay[i] = (float)(y * 64.0);  // 1/64-px units for the screen
-        s_as[i] = ws.peak_score[baseA + i];
-        s_ain[i] = inside(x, y);
-    }
-    for (int j = tid; j < nB; j += kScoreThreads) {
-        const double x = ws.peak_x[baseB + j], y = ws.peak_y[baseB + j];
-        s_bx[j] = x; s_by[j] = y;
-        s_fbx[j] = (float)(x * 64.0); s_fby[j] = (float)(y * 64.0);
-        s_bs[j] = ws.peak_score[baseB + j];
-        s_bin[j] = inside(x, y);
-    }
+    // warp-specialised prologue: warp 0 stages the A list, warp 1 the B list, warps 2-3 build the per-m tables;
+    // the other warps go straight to the barrier (the prologue is pure issue overhead for them)
     const bool screen = a.screen && a.mid_num <= kScreenMaxMid && H <= kScreenMaxDim && W <= kScreenMaxDim;
-    if (tid <= a.mid_num && tid <= kScreenMaxMid) {
-        const int m = tid;
-        // fewest samples that must exceed thre2: smallest integer >= connect_ration*m in f64, as :246 compares
-        const double need = __dmul_rn(a.connect_ration, (double)m);
-        int need_i = (int)need;
-        if ((double)need_i < need) need_i++;
-        s_maxfail[m] = (signed char)max(min(m - need_i, 127), -1);
-        s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
-        s_inv64[m] = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
-        // screen positions: up to kScreenSamples sample indices spread over the interior [m/8, m-1-m/8]
-        const int lo = m / 8, hi = m - 1 - lo;
-        const int qn = max(0, min(kScreenSamples, hi - lo + 1));
-        s_qn[m] = (unsigned char)qn;
-        for (int q = 0; q < kScreenSamples; q++)
-            s_ts[m * kScreenSamples + q] = (float)(qn > 1 ? lo + (q * (hi - lo)) / (qn - 1) : lo);
+    if (warp == 0) {
+        for (int i = lane; i < nA; i += 32) {
+            const double x = ws.peak_x[baseA + i], y = ws.peak_y[baseA + i];
+            s_ax[i] = x; s_ay[i] = y;
+            s_fax[i] = (float)(x * 64.0); s_fay[i] = (float)(y * 64.0);  // 1/64-px units for the screen
+            s_as[i] = ws.peak_score[baseA + i];
+            s_ain[i] = inside(x, y);
+        }
+    } else if (warp == 1) {
+        for (int j = lane; j < nB; j += 32) {
+            const double x = ws.peak_x[baseB + j], y = ws.peak_y[baseB + j];
+            s_bx[j] = x; s_by[j] = y;
+            s_fbx[j] = (float)(x * 64.0); s_fby[j] = (float)(y * 64.0);
+            s_bs[j] = ws.peak_score[baseB + j];
+            s_bin[j] = inside(x, y);
+        }
+    } else if (warp < 4) {
+        const int m = tid - 64;
+        if (m <= a.mid_num && m <= kScreenMaxMid) {
+            // fewest samples that must exceed thre2: smallest integer >= connect_ration*m in f64, as :246 compares
+            const double need = __dmul_rn(a.connect_ration, (double)m);
+            int need_i = (int)need;
+            if ((double)need_i < need) need_i++;
+            s_maxfail[m] = (signed char)max(min(m - need_i, 127), -1);
+            s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
+            s_inv64[m] = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
+            // screen positions: up to kScreenSamples sample indices spread over the interior [m/8, m-1-m/8]
+            const int lo = m / 8, hi = m - 1 - lo;
+            const int qn = max(0, min(kScreenSamples, hi - lo + 1));
+            s_qn[m] = (unsigned char)qn;
+            for (int q = 0; q < kScreenSamples; q++)
+                s_ts[m * kScreenSamples + q] = (float)(qn > 1 ? lo + (q * (hi - lo)) / (qn - 1) : lo);
+        }
     }
     __syncthreads();
     if (STAGE) mbar_wait(&bar, 0);
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
                     const float dx64 = s_fbx[j] - ax64, dy64 = s_fby[j] - ay64;
                     const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
                     if (n2 > 1e-6f) {
-                        const float q = sqrtf(n2) + 1.0f;
+                        const float q = n2 * rsqrtf(n2) + 1.0f;  // approximate norm + 1: m is only trusted 0.01 away from a tie
                         int m = -1;
                         if (q >= (float)a.mid_num + 0.51f) {
                             m = a.mid_num;
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
             }
         }
         const uint32_t bits = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_mask[(base >> 5) + warp] = bits;  // base is a multiple of 256: word = p / 32
+        if (lane == 0 && (base >> 5) + warp < nwords) s_mask[(base >> 5) + warp] = bits;  // word = p / 32
     }
     __syncthreads();
     // exclusive prefix of popcounts over the mask words (one warp)
