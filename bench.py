@@ -182,13 +182,13 @@ def run_ours(args, rank, world, local_rank):
     paf_d = paf_pin.to(dev, non_blocking=True)
     g = Grouper(max_batch=B, max_h=H, max_w=W, device=local_rank)
     views = g.device_tensors()
-    send = [views["n_persons"][:B], views["people_xy"][:B], views["people_score"][:B]]
-    recv = [[torch.empty_like(t) for _ in range(world)] for t in send] if (world > 1 and rank == 0) else None
+    from improved_body_parts_b200.sharding import gather_people
+    local = {"n_persons": views["n_persons"][:B], "people_xy": views["people_xy"][:B], "people_score": views["people_score"][:B]}
+    gathered = [None]
 
-    def gather():
+    def gather():  # NCCL gather of the person lists to rank 0 (rank order == image order)
         if world > 1:
-            for i, t in enumerate(send):
-                dist.gather(t, recv[i] if rank == 0 else None, dst=0)
+            gathered[0] = gather_people(local, dst=0)
 
     n_ev = 6
     stream = torch.cuda.current_stream()

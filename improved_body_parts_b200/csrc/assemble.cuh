@@ -34,7 +34,7 @@
 namespace spg {
 
 struct AssembleArgs {
-    int n_images, image_base;
+    int n_images, image_base, use_bulk;
     double len_rate, connection_tole, min_mean_score;
     int remove_recon, min_parts;
     Workspace ws;
@@ -52,6 +52,11 @@ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
                + (size_t)K * capP * sizeof(short)     // owner
                + (size_t)capR;                        // alive
     return (b + 15) & ~(size_t)15;
+}
+
+// connection tables of one image staged in shared memory (bulk copies): ij, score, norm [L][capP] + counts [L]
+__host__ __device__ inline size_t assemble_conn_bytes(int L, int capP) {
+    return (size_t)L * capP * (sizeof(uint32_t) + 2 * sizeof(double)) + (((size_t)L * sizeof(int) + 15) & ~(size_t)15);
 }
 
 struct PersonTable {
@@ -177,9 +182,18 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     const int n = a.image_base + blockIdx.x;
     const int K = ws.K, L = ws.L, capP = ws.capP, capR = ws.capR;
 
+    // shared memory: [conn_score | conn_norm | conn_ij | conn_count] of this image, then the person table
+    __shared__ uint64_t bar;
+    const size_t LC = (size_t)L * capP;
+    double *s_cs = reinterpret_cast<double *>(smem_raw);
+    double *s_cn = s_cs + LC;
+    uint32_t *s_cij = reinterpret_cast<uint32_t *>(s_cn + LC);
+    int *s_cc = reinterpret_cast<int *>(s_cij + LC);
+    unsigned char *table_base = smem_raw + assemble_conn_bytes(L, capP);
+
     PersonTable t;
     t.K = K; t.capP = capP; t.capR = capR;
-    t.sc = reinterpret_cast<double *>(smem_raw);
+    t.sc = reinterpret_cast<double *>(table_base);
     t.total = t.sc + (size_t)K * capR;
     t.maxlen = t.total + capR;
     t.id = reinterpret_cast<int *>(t.maxlen + capR);
@@ -192,6 +206,26 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     t.owner = reinterpret_cast<short *>(t.off + (K + 1));
     t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
 
+    // Everything this image needs from global memory is fetched up front -- the connection tables by the bulk-copy
+    // engine -- so that the serial limb loop below never waits on L2.
+    const size_t img_conn = (size_t)n * LC;
+    if (a.use_bulk) {
+        if (lane == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&bar, (uint32_t)(LC * (sizeof(uint32_t) + 2 * sizeof(double))));
+            bulk_g2s(s_cs, ws.conn_score + img_conn, (uint32_t)(LC * sizeof(double)), &bar);
+            bulk_g2s(s_cn, ws.conn_norm + img_conn, (uint32_t)(LC * sizeof(double)), &bar);
+            bulk_g2s(s_cij, ws.conn_ij + img_conn, (uint32_t)(LC * sizeof(uint32_t)), &bar);
+        }
+    } else {
+        for (size_t i = lane; i < LC; i += 32) {
+            s_cs[i] = ws.conn_score[img_conn + i];
+            s_cn[i] = ws.conn_norm[img_conn + i];
+            s_cij[i] = ws.conn_ij[img_conn + i];
+        }
+    }
+    for (int k = lane; k < L; k += 32) s_cc[k] = ws.conn_count[(size_t)n * L + k];
     if (lane == 0) {
         int acc = 0;
         for (int c = 0; c < K; c++) {
@@ -209,43 +243,20 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         t.alive[i] = 0;
     }
     __syncwarp();
+    if (a.use_bulk) mbar_wait(&bar, 0);
 
     int nrows = 0;
     uint32_t flags = 0;
     bool overflow = false;
 
-    // software prefetch of the next limb's first chunk keeps the L2 latency off the per-limb chain
-    auto load_limb = [&](int k, int &cc, uint32_t &ij, double &s, double &len) {
-        cc = -1; ij = 0; s = 0.0; len = 0.0;
-        if (k >= L) return;
-        const size_t slot = (size_t)n * L + k;
-        cc = ws.conn_count[slot];
-        if (lane < cc) {
-            ij = ws.conn_ij[slot * capP + lane];
-            s = ws.conn_score[slot * capP + lane];
-            len = ws.conn_norm[slot * capP + lane];
-        }
-    };
-    int cc_n; uint32_t ij_n; double s_n, len_n;
-    load_limb(0, cc_n, ij_n, s_n, len_n);
-
     for (int k = 0; k < L && !overflow; k++) {
-        const int cc = cc_n;
-        uint32_t my_ij = ij_n;
-        double my_s = s_n, my_len = len_n;
-        load_limb(k + 1, cc_n, ij_n, s_n, len_n);
+        const int cc = s_cc[k];
         if (cc < 0) continue;  // special_k (:290)
         const int A = ws.limbs[2 * k], B = ws.limbs[2 * k + 1];
-        const size_t slot = (size_t)n * L + k;
         for (int chunk = 0; chunk < cc && !overflow; chunk += 32) {
-            if (chunk > 0) {
-                const int mine = chunk + lane;
-                if (mine < cc) {
-                    my_ij = ws.conn_ij[slot * capP + mine];
-                    my_s = ws.conn_score[slot * capP + mine];
-                    my_len = ws.conn_norm[slot * capP + mine];
-                }
-            }
+            const int mine_c = min(chunk + lane, cc - 1);
+            const uint32_t my_ij = s_cij[k * capP + mine_c];
+            const double my_s = s_cs[k * capP + mine_c], my_len = s_cn[k * capP + mine_c];
             const int in_chunk = min(32, cc - chunk);
             const int ia = (int)(my_ij >> 16), jb = (int)(my_ij & 0xffff);
             const int birth = (k << 8) | (chunk + lane);

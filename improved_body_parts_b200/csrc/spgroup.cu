@@ -192,7 +192,9 @@ int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStr
     a.remove_recon = p->remove_recon;
     a.min_parts = p->min_parts;
     a.ws = h->ws;
-    const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR);
+    a.use_bulk = ((size_t)h->ws.L * h->ws.capP * sizeof(uint32_t)) % 16 == 0;  // bulk copies move multiples of 16 bytes
+    const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR) + assemble_conn_bytes(h->ws.L, h->ws.capP);
+    if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "capacities need %zu B of shared memory in assemble (limit %zu)", smem, h->smem_optin);
     SPG_CUDA(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     assemble_kernel<<<n, kAssembleThreads, smem, st>>>(a);
     h->launches++;

@@ -1,0 +1,200 @@
+"""Drop-in replacements for the reference's grouping call sites (evaluate.py:509-511).
+
+The reference has no plugin interface: ``process()`` resolves three module-level functions by name,
+
+    all_peaks                  = find_peaks(heatmap, params)                                  # evaluate.py:169
+    connection_all, special_k  = find_connections(all_peaks, paf, oriImg.shape[0], params)    # evaluate.py:206
+    subset, candidate          = find_people(connection_all, special_k, all_peaks, params)    # evaluate.py:279
+
+so the boundary is "same names, same arguments, same Python return structures".  The functions below honour it
+and run every stage on the GPU through ``libspgroup.so``; ``install(evaluate)`` rebinds the three names in an
+already imported ``evaluate`` module (INTEGRATION.md shows the launcher).  Argument meaning and quirks follow
+the reference: ``image_width`` is really the image height (evaluate.py:510), border peaks come back as integer
+coordinates, ``special_k`` limbs get ``[]``, ``candidate`` is the flattened peak table.
+
+Each stage is self-contained (it uploads what it is given), so the functions can be swapped in one at a time;
+``group()`` is the fused call for code that owns the call site and wants one device round trip.
+There is no CPU path: without the CUDA library / an sm_100 GPU these functions raise ``GroupingError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .grouping import Grouper, GroupingError, GroupResult
+from .skeleton import COCO_FROM_PART, LIMBS, NUM_PARTS
+
+_limbs: Tuple[Tuple[int, int], ...] = LIMBS
+_device = 0
+_groupers: Dict[Tuple[int, int], Grouper] = {}
+CAP_PEAKS, CAP_CANDS, CAP_ROWS = 128, 4096, 128
+
+
+def configure(limbs: Optional[Sequence[Tuple[int, int]]] = None, device: Optional[int] = None) -> None:
+    """Select the limb table (default: the Canonical ``limbs_conn``, config/config.py:94) and the CUDA device."""
+    global _limbs, _device
+    if limbs is not None:
+        _limbs = tuple((int(a), int(b)) for a, b in limbs)
+    if device is not None:
+        _device = int(device)
+    for g in _groupers.values():
+        g.close()
+    _groupers.clear()
+
+
+def _grouper(H: int, W: int) -> Grouper:
+    key = (H, W)
+    g = _groupers.get(key)
+    if g is None:
+        g = Grouper(_limbs, NUM_PARTS, COCO_FROM_PART, max_batch=1, max_h=H, max_w=W, max_peaks_per_part=CAP_PEAKS,
+                    max_cands_per_limb=CAP_CANDS, max_person_rows=CAP_ROWS, device=_device)
+        _groupers[key] = g
+    return g
+
+
+def _check(r: GroupResult) -> None:
+    if r.status[0]:
+        raise GroupingError(f"grouping capacity exceeded or invalid sample index (status {int(r.status[0]):#x}); "
+                            f"capacities: {CAP_PEAKS} peaks/part, {CAP_CANDS} candidates/limb, {CAP_ROWS} person rows")
+
+
+def _maps_to_device(hwc: np.ndarray, channels: int, dtype):
+    import torch
+    arr = np.ascontiguousarray(np.asarray(hwc)[:, :, :channels].transpose(2, 0, 1), dtype)
+    return torch.from_numpy(arr).to(f"cuda:{_device}")[None]
+
+
+def _upload_peaks(g: Grouper, all_peaks) -> None:
+    counts = [len(p) for p in all_peaks]
+    flat = [t for part in all_peaks for t in part]
+    g.upload_peaks(0, counts, [float(t[0]) for t in flat], [float(t[1]) for t in flat], [np.float32(t[2]) for t in flat])
+
+
+# ---- the three reference functions ---------------------------------------------------------------------
+def find_peaks(heatmap_avg, params):
+    """evaluate.py:169-203.  ``heatmap_avg [H,W,>=18]`` -> list[18] of [(x, y, score, id), ...]."""
+    H, W = heatmap_avg.shape[:2]
+    g = _grouper(H, W)
+    g.nms_peaks(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), params)  # the cast is evaluate.py:173
+    r = g.fetch(1)
+    _check(r)
+    return r.as_reference_structures(0)[0]
+
+
+def find_connections(all_peaks, paf_avg, image_width, params):
+    """evaluate.py:206-276.  ``paf_avg [H,W,L]`` float32 or float64 -> (connection_all, special_k)."""
+    H, W = paf_avg.shape[:2]
+    g = _grouper(H, W)
+    _upload_peaks(g, all_peaks)
+    dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
+    g.limb_score(_maps_to_device(paf_avg, len(_limbs), dtype), image_width, params)
+    g.limb_match(1, params)
+    r = g.fetch(1)
+    _check(r)
+    # ids in the rows are those of the caller's all_peaks (:267), not positions in our tables
+    _, conns, special, _, _ = r.as_reference_structures(0)
+    for k, rows in enumerate(conns):
+        if isinstance(rows, list) or not len(rows):
+            continue
+        a, b = _limbs[k]
+        rows[:, 0] = [all_peaks[a][int(i)][3] for i in rows[:, 3]]
+        rows[:, 1] = [all_peaks[b][int(j)][3] for j in rows[:, 4]]
+    return conns, special
+
+
+def find_people(connection_all, special_k, all_peaks, params):
+    """evaluate.py:279-498 -> (subset [P,20,2] float64, candidate [N,4] float64)."""
+    g = next(iter(_groupers.values())) if _groupers else _grouper(128, 128)  # assembly does not depend on the map size
+    _upload_peaks(g, all_peaks)
+    special = set(int(k) for k in special_k)
+    counts, ij, sc, nm = [], [], [], []
+    for k, rows in enumerate(connection_all):
+        if k in special:
+            counts.append(-1)
+            continue
+        rows = np.asarray(rows, np.float64).reshape(-1, 6)
+        counts.append(len(rows))
+        ij.append(rows[:, 3:5].astype(np.int32))
+        sc.append(rows[:, 2])
+        nm.append(rows[:, 5])
+    g.upload_connections(0, counts, np.concatenate(ij) if ij else np.zeros((0, 2), np.int32),
+                         np.concatenate(sc) if sc else np.zeros(0), np.concatenate(nm) if nm else np.zeros(0))
+    g.assemble(1, params)
+    r = g.fetch(1)
+    _check(r)
+    subset = r.subset[0, :int(r.n_persons[0])].copy()
+    candidate = np.array([item for sublist in all_peaks for item in sublist])  # evaluate.py:283, verbatim semantics
+    # subset holds positions in the flattened table; the reference stores the peaks' own ids there (equal unless
+    # the caller renumbered all_peaks)
+    flat_ids = [t[3] for part in all_peaks for t in part]
+    if flat_ids != list(range(len(flat_ids))):
+        ids = np.asarray(flat_ids, np.float64)
+        sel = subset[:, :-2, 0] >= 0
+        subset[:, :-2, 0][sel] = ids[subset[:, :-2, 0][sel].astype(int)]
+    return subset, candidate
+
+
+def group(heatmap_avg, paf_avg, image_extent, params):
+    """Fused peaks -> connections -> people: one upload, four kernels, one download.
+
+    Returns ``(all_peaks, connection_all, special_k, subset, candidate)`` exactly as the three calls would."""
+    H, W = heatmap_avg.shape[:2]
+    g = _grouper(H, W)
+    dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
+    g.group_device(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _maps_to_device(paf_avg, len(_limbs), dtype),
+                   image_extent, params)
+    r = g.fetch(1)
+    _check(r)
+    return r.as_reference_structures(0)
+
+
+def keypoints(subset, candidate):
+    """Tail of process() (evaluate.py:523-543): [(17 x (x, y) in COCO order, score)]."""
+    out = []
+    for row in subset:
+        pts = []
+        for part in COCO_FROM_PART:
+            idx = row[part, 0]
+            pts.append((0, 0) if idx == -1 else tuple(candidate[int(idx)][:2]))
+        out.append((pts, 1 - 1.0 / row[-2, 0]))
+    return out
+
+
+def keypoint_heatmap_nms(heat, kernel: int = 3, thre: float = 0.1):
+    """utils/util.py:177-183 -- the one seam demo_image.py offers (:213).  ``heat [1,C,H,W]`` tensor -> ``heat * keep``.
+
+    Peaks come from the CUDA NMS kernel; the masked map is rebuilt from them (zeros elsewhere)."""
+    import torch
+    if kernel != 3:
+        raise GroupingError("only the 3x3 NMS the reference uses is implemented")
+    if heat.dim() != 4 or heat.shape[0] != 1:
+        raise GroupingError("expected a [1,C,H,W] tensor")
+    C, H, W = heat.shape[1:]
+    g = Grouper(((0, 0),), C, (0,), max_batch=1, max_h=H, max_w=W, max_peaks_per_part=CAP_PEAKS,
+                device=_device) if C != NUM_PARTS else _grouper(H, W)
+    src = heat.to(f"cuda:{_device}", torch.float32).contiguous()
+    g.nms_peaks(src, dict(thre1=float(thre), offset_radius=0))
+    r = g.fetch(1)
+    _check(r)
+    out = torch.zeros_like(src)
+    for c in range(C):
+        n = int(min(r.peak_count[0, c], r.peak_anchor.shape[2]))
+        if n:
+            a = r.peak_anchor[0, c, :n].astype(np.int64)
+            ys = torch.as_tensor((a >> 16) & 0x7fff, device=src.device)
+            xs = torch.as_tensor(a & 0xffff, device=src.device)
+            out[0, c, ys, xs] = src[0, c, ys, xs]
+    if C != NUM_PARTS:
+        g.close()
+    return out.to(heat.device)
+
+
+def install(evaluate_module) -> None:
+    """Rebind ``find_peaks / find_connections / find_people`` of an imported reference ``evaluate`` module.
+
+    ``limbSeq`` is taken from the module (evaluate.py:54) so alternative skeletons keep working."""
+    configure(limbs=getattr(evaluate_module, "limbSeq", _limbs))
+    evaluate_module.find_peaks = find_peaks
+    evaluate_module.find_connections = find_connections
+    evaluate_module.find_people = find_people
