@@ -43,15 +43,15 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
 // number of register slots so that limbs with few survivors do not pay for eight.  The accepted row's (i, j)
 // and score are stored by the lane that owns the winner; limb lengths are filled in afterwards in parallel.
 template <int NS>
-__device__ __forceinline__ int match_rounds_keys(const Workspace &ws, size_t cbase, size_t obase, int nC, int lim, int lane) {
+__device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsigned long long (&key8)[kMatchRegCands],
+                                                 const double (&sc8)[kMatchRegCands], size_t obase, int nC, int lim, int lane) {
     unsigned long long key[NS];  // 0 = dead / absent
     double sc[NS];
 #pragma unroll
     for (int r = 0; r < NS; r++) {
-        const int cidx = lane + 32 * r;
-        const bool ok = cidx < nC;
-        key[r] = ok ? ws.cand_key[cbase + cidx] : 0ull;
-        sc[r] = ok ? ws.cand_score[cbase + cidx] : 0.0;
+        const bool ok = lane + 32 * r < nC;  // the registers were loaded speculatively, before nC was known
+        key[r] = ok ? key8[r] : 0ull;
+        sc[r] = sc8[r];
     }
     int m = 0;
     while (m < lim) {
@@ -90,16 +90,28 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
     const int k = w % ws.L;
     const int n = a.image_base + w / ws.L;
     const size_t slot = (size_t)n * ws.L + k;
+    const size_t cbase = slot * ws.capC;
+    const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
+    // One round trip to L2 instead of three: the survivor keys/scores are fetched speculatively (any slot below capC
+    // is valid memory; slots >= nC are masked later) together with the three counters they would otherwise wait for.
+    unsigned long long key8[kMatchRegCands];
+    double sc8[kMatchRegCands];
+#pragma unroll
+    for (int r = 0; r < kMatchRegCands; r++) {
+        const int cidx = lane + 32 * r;
+        const bool in = a.keys_valid && cidx < ws.capC;
+        key8[r] = in ? ws.cand_key[cbase + cidx] : 0ull;
+        sc8[r] = in ? ws.cand_score[cbase + cidx] : 0.0;
+    }
     const int nC = ws.cand_count[slot];
+    const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
     if (nC < 0) {  // special_k
         if (lane == 0) ws.conn_count[slot] = -1;
         return;
     }
-    const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
-    const int nA = min(ws.peak_count[(size_t)n * ws.K + pa], ws.capP);
-    const int nB = min(ws.peak_count[(size_t)n * ws.K + pb], ws.capP);
+    const int nA = min(cntA, ws.capP);
+    const int nB = min(cntB, ws.capP);
     const int lim = min(nA, nB);
-    const size_t cbase = slot * ws.capC;
     const size_t obase = slot * ws.capP;
     const size_t baseA = ((size_t)n * ws.K + pa) * ws.capP, baseB = ((size_t)n * ws.K + pb) * ws.capP;
 
@@ -118,14 +130,14 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
         // ---- fast path, f32 planes: one 64-bit key per survivor, all in registers -----------------------
         switch (nslots) {
             case 0: break;
-            case 1: m = match_rounds_keys<1>(ws, cbase, obase, nC, lim, lane); break;
-            case 2: m = match_rounds_keys<2>(ws, cbase, obase, nC, lim, lane); break;
-            case 3: m = match_rounds_keys<3>(ws, cbase, obase, nC, lim, lane); break;
-            case 4: m = match_rounds_keys<4>(ws, cbase, obase, nC, lim, lane); break;
-            case 5: m = match_rounds_keys<5>(ws, cbase, obase, nC, lim, lane); break;
-            case 6: m = match_rounds_keys<6>(ws, cbase, obase, nC, lim, lane); break;
-            case 7: m = match_rounds_keys<7>(ws, cbase, obase, nC, lim, lane); break;
-            default: m = match_rounds_keys<8>(ws, cbase, obase, nC, lim, lane); break;
+            case 1: m = match_rounds_keys<1>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 2: m = match_rounds_keys<2>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 3: m = match_rounds_keys<3>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 4: m = match_rounds_keys<4>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 5: m = match_rounds_keys<5>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 6: m = match_rounds_keys<6>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 7: m = match_rounds_keys<7>(ws, key8, sc8, obase, nC, lim, lane); break;
+            default: m = match_rounds_keys<8>(ws, key8, sc8, obase, nC, lim, lane); break;
         }
         __syncwarp();  // the rows were written by different lanes of this warp
         for (int c = lane; c < m; c += 32) {  // limb lengths (the reference's `norm`, :225) in parallel

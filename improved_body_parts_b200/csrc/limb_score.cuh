@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     __shared__ int s_count;
     __shared__ uint32_t s_flags;
     __shared__ int s_total_surv;
+    __shared__ uint32_t s_magic;
 
     const Workspace &ws = a.ws;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
             for (int q = 0; q < kScreenSamples; q++)
                 s_ts[m * kScreenSamples + q] = (float)(qn > 1 ? lo + (q * (hi - lo)) / (qn - 1) : lo);
         }
+        if (tid == 64 + 63) s_magic = nB > 1 ? 0xffffffffu / (uint32_t)nB + 1u : 0u;  // ceil(2^32 / nB)
     }
     __syncthreads();
     if (STAGE) mbar_wait(&bar, 0);
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     const T thre2 = (T)a.thre2;  // f32 plane: `> thre2` is an f32 compare against (float)thre2
 
     // ---------------- phase A: conservative screen ----------------
-    const uint32_t magic = nB > 1 ? (uint32_t)((0x100000000ull + nB - 1) / nB) : 0;  // p / nB == umulhi(p, magic), p < 2^14
+    const uint32_t magic = s_magic;  // p / nB == umulhi(p, magic) for p < 2^14
     for (int base = 0; base < npairs; base += kScoreThreads) {
         const int p = base + tid;
         bool keep = false;

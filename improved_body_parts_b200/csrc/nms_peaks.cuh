@@ -93,7 +93,7 @@ __device__ __forceinline__ void refine_box(const float *__restrict__ plane, int 
 __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
-    __shared__ int s_count;
+    __shared__ int s_count, s_nq;
 
     const Workspace &ws = a.ws;
     const int tid = threadIdx.x;
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
     float *buf1 = buf0 + ((band_floats + 31) & ~(size_t)31);
     uint32_t *s_list = reinterpret_cast<uint32_t *>(buf1 + ((band_floats + 31) & ~(size_t)31));
     uint32_t *s_sorted = s_list + ws.capP;
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_sorted + ws.capP);  // float4 groups of the band worth testing
 
     const int nb = (H + br - 1) / br;
     if (tid == 0) {
@@ -144,23 +145,40 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
         }
         const int y0 = b * br, y1 = min(y0 + br, H);
         if ((W & 3) == 0) {
-            // float4 groups; a group is rejected with one compare when none of its values reaches thre1.
-            // Neighbour rows/columns are CLAMPED to the image: a clamped neighbour is a pixel that is already
-            // inside the clipped 3x3 window (or the pixel itself), so the window max is unchanged.
+            // Pass 1: float4 groups; a group is dropped with one compare when none of its values reaches thre1 (the
+            // common case); the others are queued, warp-aggregated.  Pass 2 runs the 8-neighbour test densely over
+            // the queue, so warps do not drag idle lanes through it.
             const int W4 = W >> 2;
             const int groups = (y1 - y0) * W4;
-            // (row, quad) of this thread's first group, then advanced by kNmsThreads groups without dividing
-            int r = tid / W4, xq = tid - r * W4;
-            const int dr = kNmsThreads / W4, dq = kNmsThreads - dr * W4;
-            for (int g = tid; g < groups; g += kNmsThreads, r += dr, xq += dq) {
-                if (xq >= W4) { xq -= W4; r++; }
+            if (tid == 0) s_nq = 0;
+            __syncthreads();
+            for (int g0 = 0; g0 < groups; g0 += kNmsThreads) {
+                const int g = g0 + tid;
+                bool act = false;
+                if (g < groups) {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(buf + (size_t)(y0 - lo) * W + 4 * (size_t)g);
+                    act = fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)) >= a.thr;
+                }
+                const uint32_t am = __ballot_sync(0xffffffffu, act);
+                if (am) {
+                    int base = 0;
+                    if ((tid & 31) == 0) base = atomicAdd(&s_nq, __popc(am));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (act) s_queue[base + __popc(am & ((1u << (tid & 31)) - 1u))] = (uint16_t)g;
+                }
+            }
+            __syncthreads();
+            const int nq = s_nq;
+            // Neighbour rows/columns are CLAMPED to the image: a clamped neighbour is a pixel that is already
+            // inside the clipped 3x3 window (or the pixel itself), so the window max is unchanged.
+            for (int q = tid; q < nq; q += kNmsThreads) {
+                const int g = s_queue[q];
+                const int r = g / W4, xq = g - r * W4;
                 const int y = y0 + r, x0 = 4 * xq;
                 const float *rc = buf + (size_t)(y - lo) * W;
-                const float4 c4 = *reinterpret_cast<const float4 *>(rc + x0);
-                const float m = fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w));
-                if (!(m >= a.thr)) continue;
                 const float *ru = buf + (size_t)(max(y - 1, 0) - lo) * W;
                 const float *rd = buf + (size_t)(min(y + 1, H - 1) - lo) * W;
+                const float4 c4 = *reinterpret_cast<const float4 *>(rc + x0);
                 const float4 u4 = *reinterpret_cast<const float4 *>(ru + x0);
                 const float4 d4 = *reinterpret_cast<const float4 *>(rd + x0);
                 const int xl = max(x0 - 1, 0), xr = min(x0 + 4, W - 1);
@@ -243,7 +261,8 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
 
 inline size_t nms_smem_bytes(int band_rows, int W, int capP) {
     const size_t band_floats = (((size_t)(band_rows + 2) * W) + 31) & ~(size_t)31;
-    return 2 * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t);
+    const size_t queue = (((size_t)band_rows * W / 4) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    return 2 * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t) + queue;
 }
 
 }  // namespace spg
