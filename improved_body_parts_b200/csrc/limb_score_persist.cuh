@@ -1,0 +1,307 @@
+// limb_score_persist.cuh -- K2a, persistent warp-specialised form (f32 planes that fit a 3-deep ring).
+//
+// Same arithmetic and outputs as limb_score_kernel (limb_score.cuh: conservative f32 screen, then the
+// reference's exact evaluation of the survivors, evaluate.py:211-255); different schedule.  The one-CTA-per-
+// (image, limb) kernel pays a prologue per item, serialises load -> screen -> exact inside a CTA and leaves
+// issue slots idle at every barrier.  Here one CTA per SM stays resident and walks over its items
+// (item = image * L + limb, strided by the grid) through a ring of 3 plane slots with three roles:
+//
+//   loader   (warp 0)       waits for a free slot, stages the item's two end-point lists (every slot of the
+//                           capacity is fetched, so the loads do not wait for the counters), then issues the
+//                           plane's bulk copy (TMA, SASS UBLKCP) onto the slot's `full` mbarrier.  Runs up to
+//                           two items ahead.
+//   screeners (warps 1-27)  phase A of item j: one thread per pair, survivors appended (warp-aggregated) to one
+//                           of two survivor lists; each warp arrives on `a_done`.
+//   scorers  (warps 28-31)  phase B of item j-1, concurrently with the screeners working on item j: one thread
+//                           per survivor, candidates appended to global memory; the last warp publishes the
+//                           counters, recycles the list and every warp arrives on `b_done` / `slot_free`.
+//
+// All hand-offs are mbarriers (no __syncthreads after start-up); the per-m tables are built once per CTA.
+#pragma once
+
+#include "limb_score.cuh"
+
+namespace spg {
+
+constexpr int kPersistThreads = 1024;
+constexpr int kPersistSlots = 3;
+constexpr int kScorerWarps = 4;
+constexpr int kScreenWarps = kPersistThreads / 32 - 1 - kScorerWarps;  // 27
+constexpr int kPersistMaxCapP = 64;
+
+struct PersistHdr {
+    int nA, nB, npairs, n, k, special;
+    uint32_t magic;
+    int pad;
+};
+
+__host__ __device__ inline size_t persist_peaks_bytes(int capP) {
+    return (((size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2)) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t persist_tables_bytes() {
+    return (((size_t)(kScreenMaxMid + 1) * (sizeof(double) + (kScreenSamples + 1) * sizeof(float) + 2)) + 15) & ~(size_t)15;
+}
+inline size_t persist_smem_bytes(size_t plane_bytes, int capP) {
+    const size_t plane = (plane_bytes + 127) & ~(size_t)127;
+    return kPersistSlots * plane + kPersistSlots * persist_peaks_bytes(capP) + persist_tables_bytes() +
+           2 * (size_t)capP * capP * sizeof(uint16_t) + 256;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct PeakSlot {
+    double *ax, *ay, *bx, *by;
+    float *as, *bs, *fax, *fay, *fbx, *fby;
+    unsigned char *ain, *bin;
+};
+__device__ __forceinline__ PeakSlot peak_slot(unsigned char *base, int capP) {
+    PeakSlot p;
+    p.ax = reinterpret_cast<double *>(base);
+    p.ay = p.ax + capP;
+    p.bx = p.ay + capP;
+    p.by = p.bx + capP;
+    p.as = reinterpret_cast<float *>(p.by + capP);
+    p.bs = p.as + capP;
+    p.fax = p.bs + capP;
+    p.fay = p.fax + capP;
+    p.fbx = p.fay + capP;
+    p.fby = p.fbx + capP;
+    p.ain = reinterpret_cast<unsigned char *>(p.fby + capP);
+    p.bin = p.ain + capP;
+    return p;
+}
+
+__global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar_full[kPersistSlots], bar_free[kPersistSlots], bar_adone[2], bar_bdone[2];
+    __shared__ PersistHdr s_hdr[kPersistSlots];
+    __shared__ int s_nsurv[2], s_ncand[2], s_done[2];
+    __shared__ uint32_t s_flags[2];
+
+    using T = float;
+    const Workspace &ws = a.ws;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W, capP = ws.capP, L = ws.L;
+    const size_t plane_bytes = (size_t)H * W * sizeof(T);
+    const size_t plane_stride = (plane_bytes + 127) & ~(size_t)127;
+    unsigned char *peaks_base = smem_raw + kPersistSlots * plane_stride;
+    const size_t peaks_stride = persist_peaks_bytes(capP);
+    unsigned char *tables = peaks_base + kPersistSlots * peaks_stride;
+    double *s_rcp = reinterpret_cast<double *>(tables);
+    float *s_ts = reinterpret_cast<float *>(s_rcp + (kScreenMaxMid + 1));
+    float *s_inv64 = s_ts + (size_t)(kScreenMaxMid + 1) * kScreenSamples;
+    signed char *s_maxfail = reinterpret_cast<signed char *>(s_inv64 + (kScreenMaxMid + 1));
+    unsigned char *s_qn = reinterpret_cast<unsigned char *>(s_maxfail + (kScreenMaxMid + 1));
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(tables + persist_tables_bytes());  // [2][capP*capP]
+    const int list_stride = capP * capP;
+
+    // ---- one-time set-up
+    if (tid == 0) {
+        for (int s = 0; s < kPersistSlots; s++) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_free[s], kScorerWarps);
+        }
+        for (int q = 0; q < 2; q++) {
+            mbar_init(&bar_adone[q], kScreenWarps);
+            mbar_init(&bar_bdone[q], kScorerWarps);
+            s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0;
+        }
+        fence_mbar_init();
+    }
+    if (tid >= 32 && tid < 32 + kScreenMaxMid + 1) {
+        const int m = tid - 32;
+        const double need = __dmul_rn(a.connect_ration, (double)m);  // :246 compares in f64
+        int need_i = (int)need;
+        if ((double)need_i < need) need_i++;
+        s_maxfail[m] = (signed char)max(min(m - need_i, 127), -1);
+        s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
+        s_inv64[m] = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;
+        const int lo = m / 8, hi = m - 1 - lo;
+        const int qn = max(0, min(kScreenSamples, hi - lo + 1));
+        s_qn[m] = (unsigned char)qn;
+        for (int q = 0; q < kScreenSamples; q++)
+            s_ts[m * kScreenSamples + q] = (float)(qn > 1 ? lo + (q * (hi - lo)) / (qn - 1) : lo);
+    }
+    __syncthreads();
+
+    const int G = gridDim.x;
+    const int nj = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const bool screen = a.screen && a.mid_num <= kScreenMaxMid && H <= kScreenMaxDim && W <= kScreenMaxDim;
+    const T thre2 = (T)a.thre2;
+
+    if (warp == 0) {
+        // =========================== loader ===========================
+        for (int j = 0; j < nj; j++) {
+            const int s = j % kPersistSlots;
+            if (j >= kPersistSlots) mbar_wait(&bar_free[s], ((j / kPersistSlots) - 1) & 1);
+            const int item = (int)blockIdx.x + j * G;
+            const int n_local = item / L, k = item - n_local * L;
+            const int n = a.image_base + n_local;
+            const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
+            const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
+            const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
+            PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
+            for (int e = lane; e < capP; e += 32) {  // whole capacity: independent of the counters
+                const double xa = ws.peak_x[baseA + e], ya = ws.peak_y[baseA + e];
+                const double xb = ws.peak_x[baseB + e], yb = ws.peak_y[baseB + e];
+                const float sa = ws.peak_score[baseA + e], sb = ws.peak_score[baseB + e];
+                ps.ax[e] = xa; ps.ay[e] = ya; ps.bx[e] = xb; ps.by[e] = yb;
+                ps.as[e] = sa; ps.bs[e] = sb;
+                ps.fax[e] = (float)(xa * 64.0); ps.fay[e] = (float)(ya * 64.0);
+                ps.fbx[e] = (float)(xb * 64.0); ps.fby[e] = (float)(yb * 64.0);
+                ps.ain[e] = xa >= 1.0 && xa <= (double)(W - 2) && ya >= 1.0 && ya <= (double)(H - 2);
+                ps.bin[e] = xb >= 1.0 && xb <= (double)(W - 2) && yb >= 1.0 && yb <= (double)(H - 2);
+            }
+            const int nA = min(cntA, capP), nB = min(cntB, capP);
+            const bool special = nA == 0 || nB == 0;
+            if (lane == 0) {
+                PersistHdr h;
+                h.nA = nA; h.nB = nB; h.npairs = special ? 0 : nA * nB; h.n = n; h.k = k; h.special = special;
+                h.magic = nB > 1 ? 0xffffffffu / (uint32_t)nB + 1u : 0u;
+                h.pad = 0;
+                s_hdr[s] = h;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (special) {
+                    mbar_arrive(&bar_full[s]);
+                } else {
+                    const unsigned char *gplane = reinterpret_cast<const unsigned char *>(
+                        reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride);
+                    unsigned char *dst = smem_raw + s * plane_stride;
+                    mbar_expect_tx(&bar_full[s], (uint32_t)plane_bytes);
+                    for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
+                        const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
+                        bulk_g2s(dst + off, gplane + off, bytes, &bar_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp <= kScreenWarps) {
+        // =========================== screeners (phase A) ===========================
+        const int tidA = tid - 32;
+        constexpr int kStrideA = kScreenWarps * 32;
+        for (int j = 0; j < nj; j++) {
+            const int s = j % kPersistSlots, q = j & 1;
+            mbar_wait(&bar_full[s], (j / kPersistSlots) & 1);
+            if (j >= 2) mbar_wait(&bar_bdone[q], ((j >> 1) - 1) & 1);
+            const PersistHdr h = s_hdr[s];
+            const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
+            const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
+            uint16_t *list = s_list + q * list_stride;
+            const int nB = h.nB;
+            for (int base = 0; base < h.npairs; base += kStrideA) {
+                const int p = base + tidA;
+                bool keep = false;
+                if (p < h.npairs) {
+                    keep = true;
+                    if (screen) {
+                        const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
+                        const int jj = p - i * nB;
+                        if (ps.ain[i] && ps.bin[jj]) {
+                            const float ax64 = ps.fax[i], ay64 = ps.fay[i];
+                            const float dx64 = ps.fbx[jj] - ax64, dy64 = ps.fby[jj] - ay64;
+                            const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
+                            if (n2 > 1e-6f) {
+                                const float qf = n2 * rsqrtf(n2) + 1.0f;  // approximate norm + 1
+                                int m = -1;
+                                if (qf >= (float)a.mid_num + 0.51f) {
+                                    m = a.mid_num;
+                                } else {
+                                    const float r = rintf(qf);
+                                    if (fabsf(qf - r) < 0.49f) m = min((int)r, a.mid_num);  // else uncertain -> survive
+                                }
+                                if (m >= 1) {
+                                    const int maxfail = s_maxfail[m];
+                                    const int qn = s_qn[m];
+                                    const float inv = s_inv64[m];
+                                    const float sx64 = dx64 * inv, sy64 = dy64 * inv;
+                                    const float *ts = s_ts + m * kScreenSamples;
+                                    int fails = 0;
+                                    for (int q2 = 0; q2 < qn; q2++) {
+                                        const float tf = ts[q2];
+                                        const int xs = __float2int_rn(__fmaf_rn(tf, sx64, ax64));
+                                        const int ys = __float2int_rn(__fmaf_rn(tf, sy64, ay64));
+                                        const unsigned cx = (unsigned)(xs + 33) & 63u, cy = (unsigned)(ys + 33) & 63u;
+                                        const T v = plane[((ys + 32) >> 6) * W + ((xs + 32) >> 6)];
+                                        fails += (min(cx, cy) > 2u) && !(v > thre2);
+                                    }
+                                    keep = fails <= maxfail;
+                                }
+                            }
+                        }
+                    }
+                }
+                const uint32_t km = __ballot_sync(0xffffffffu, keep);
+                if (km) {
+                    int at = 0;
+                    if (lane == 0) at = atomicAdd(&s_nsurv[q], __popc(km));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (keep) list[at + __popc(km & ((1u << lane) - 1u))] = (uint16_t)p;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_adone[q]);
+        }
+    } else {
+        // =========================== scorers (phase B) ===========================
+        const int tidB = tid - (kScreenWarps + 1) * 32;
+        constexpr int kStrideB = kScorerWarps * 32;
+        for (int j = 0; j < nj; j++) {
+            const int s = j % kPersistSlots, q = j & 1;
+            mbar_wait(&bar_adone[q], (j >> 1) & 1);
+            mbar_wait(&bar_full[s], (j / kPersistSlots) & 1);  // already complete; makes the plane visible to this warp
+            const PersistHdr h = s_hdr[s];
+            const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
+            const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
+            const uint16_t *list = s_list + q * list_stride;
+            const int ns = s_nsurv[q];
+            const int nB = h.nB;
+            const size_t slot = (size_t)h.n * L + h.k;
+            const size_t out_base = slot * ws.capC;
+            PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
+            for (int t = tidB; t < ns; t += kStrideB) {
+                const int p = list[t];
+                const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
+                const int jj = p - i * nB;
+                double score, prio;
+                bool bad = false;
+                const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
+                if (bad) atomicOr(&s_flags[q], kStSampleIndex);
+                if (ok) {
+                    const int pos = atomicAdd(&s_ncand[q], 1);
+                    if (pos < ws.capC) {
+                        const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)jj;
+                        ws.cand_prio[out_base + pos] = prio;
+                        ws.cand_score[out_base + pos] = score;
+                        ws.cand_ij[out_base + pos] = ij;
+                        const uint32_t b = __float_as_uint((float)prio);
+                        const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                        ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();  // this warp's candidate appends before its "done" tick (and the other warps' after it)
+                const bool last = atomicAdd(&s_done[q], 1) == kScorerWarps - 1;
+                __threadfence_block();
+                if (last) {  // last scorer warp of this item: publish + recycle
+                    const int total = s_ncand[q];
+                    ws.cand_count[slot] = h.special ? -1 : min(total, ws.capC);
+                    if (ws.surv_count) ws.surv_count[slot] = ns;
+                    uint32_t f = s_flags[q];
+                    if (total > ws.capC) f |= kStCandOverflow;
+                    if (f) atomicOr(&ws.status[h.n], f);
+                    s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0;
+                }
+                mbar_arrive(&bar_bdone[q]);
+                mbar_arrive(&bar_free[s]);
+            }
+        }
+    }
+}
+
+}  // namespace spg

@@ -90,10 +90,10 @@ __device__ __forceinline__ void refine_box(const float *__restrict__ plane, int 
     sc = __fdiv_rn(s32, (float)N);  // score_box.mean() stays f32
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
+__global__ void __launch_bounds__(kNmsThreads, 3) nms_peaks_kernel(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
-    __shared__ int s_count, s_nq;
+    __shared__ int s_count;
 
     const Workspace &ws = a.ws;
     const int tid = threadIdx.x;
@@ -103,14 +103,15 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
     const int H = a.H, W = a.W, br = a.band_rows;
     const float *plane = a.heat + (int64_t)n_local * a.img_stride + (int64_t)c * a.chan_stride;
 
-    const size_t band_floats = (size_t)(br + 2) * W;
+    const int nb = (H + br - 1) / br;
+    // one band (whole plane resident): a single buffer without halo rows; else two band buffers with a halo row each side
+    const size_t band_floats = nb == 1 ? (size_t)H * W : (size_t)(br + 2) * W;
     float *buf0 = reinterpret_cast<float *>(smem_raw);
-    float *buf1 = buf0 + ((band_floats + 31) & ~(size_t)31);
+    float *buf1 = nb == 1 ? buf0 : buf0 + ((band_floats + 31) & ~(size_t)31);
     uint32_t *s_list = reinterpret_cast<uint32_t *>(buf1 + ((band_floats + 31) & ~(size_t)31));
     uint32_t *s_sorted = s_list + ws.capP;
     uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_sorted + ws.capP);  // float4 groups of the band worth testing
 
-    const int nb = (H + br - 1) / br;
     if (tid == 0) {
         s_count = 0;
         if (a.use_bulk) {
@@ -148,31 +149,31 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
             // Pass 1: float4 groups; a group is dropped with one compare when none of its values reaches thre1 (the
             // common case); the others are queued, warp-aggregated.  Pass 2 runs the 8-neighbour test densely over
             // the queue, so warps do not drag idle lanes through it.
+            // Each warp owns a contiguous slice of the band's groups and a private queue, so the two passes need no
+            // block barrier (neighbour rows are read-only in the band buffer).
             const int W4 = W >> 2;
             const int groups = (y1 - y0) * W4;
-            if (tid == 0) s_nq = 0;
-            __syncthreads();
-            for (int g0 = 0; g0 < groups; g0 += kNmsThreads) {
-                const int g = g0 + tid;
+            const int lane = tid & 31, warp = tid >> 5;
+            const int gpw = (groups + (kNmsThreads / 32) - 1) / (kNmsThreads / 32);  // groups per warp
+            const int g_lo = warp * gpw, g_hi = min(g_lo + gpw, groups);
+            uint16_t *wq = s_queue + g_lo;  // at most gpw entries
+            int nq = 0;                     // warp-uniform
+            for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
+                const int g = g0 + lane;
                 bool act = false;
-                if (g < groups) {
+                if (g < g_hi) {
                     const float4 c4 = *reinterpret_cast<const float4 *>(buf + (size_t)(y0 - lo) * W + 4 * (size_t)g);
                     act = fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)) >= a.thr;
                 }
                 const uint32_t am = __ballot_sync(0xffffffffu, act);
-                if (am) {
-                    int base = 0;
-                    if ((tid & 31) == 0) base = atomicAdd(&s_nq, __popc(am));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (act) s_queue[base + __popc(am & ((1u << (tid & 31)) - 1u))] = (uint16_t)g;
-                }
+                if (act) wq[nq + __popc(am & ((1u << lane) - 1u))] = (uint16_t)g;
+                nq += __popc(am);
             }
-            __syncthreads();
-            const int nq = s_nq;
+            __syncwarp();
             // Neighbour rows/columns are CLAMPED to the image: a clamped neighbour is a pixel that is already
             // inside the clipped 3x3 window (or the pixel itself), so the window max is unchanged.
-            for (int q = tid; q < nq; q += kNmsThreads) {
-                const int g = s_queue[q];
+            for (int q = lane; q < nq; q += 32) {
+                const int g = wq[q];
                 const int r = g / W4, xq = g - r * W4;
                 const int y = y0 + r, x0 = 4 * xq;
                 const float *rc = buf + (size_t)(y - lo) * W;
@@ -259,10 +260,11 @@ __global__ void __launch_bounds__(kNmsThreads, 5) nms_peaks_kernel(NmsArgs a) {
     }
 }
 
-inline size_t nms_smem_bytes(int band_rows, int W, int capP) {
-    const size_t band_floats = (((size_t)(band_rows + 2) * W) + 31) & ~(size_t)31;
-    const size_t queue = (((size_t)band_rows * W / 4) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    return 2 * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t) + queue;
+inline size_t nms_smem_bytes(int band_rows, int H, int W, int capP) {
+    const bool single = band_rows >= H;
+    const size_t band_floats = ((single ? (size_t)H * W : (size_t)(band_rows + 2) * W) + 31) & ~(size_t)31;
+    const size_t queue = (((size_t)std::min(band_rows, H) * W / 4 + 8) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    return (single ? 1 : 2) * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t) + queue;
 }
 
 }  // namespace spg

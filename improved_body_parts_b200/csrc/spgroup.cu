@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "limb_match.cuh"
 #include "limb_score.cuh"
+#include "limb_score_persist.cuh"
 #include "nms_peaks.cuh"
 
 using namespace spg;
@@ -41,6 +42,7 @@ struct spg_handle {
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
+    int persist = 1;  // persistent warp-specialised limb_score when it applies (SPG_SCORE_PERSIST=0 turns it off)
     int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
@@ -112,13 +114,14 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.chan_stride = chan_stride;
     a.H = H;
     a.W = W;
-    a.band_rows = std::max(4, std::min(H, 4096 / W));
+    // whole plane resident when it leaves room for 3 CTAs per SM, else double-buffered bands of ~16 KB
+    a.band_rows = ((size_t)H * W * sizeof(float) <= 72 * 1024) ? H : std::max(4, std::min(H, 4096 / W));
     a.radius = p->offset_radius;
     a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
     a.image_base = base;
     a.thr = (float)p->thre1;
     a.ws = h->ws;
-    const size_t smem = nms_smem_bytes(a.band_rows, W, h->ws.capP);
+    const size_t smem = nms_smem_bytes(a.band_rows, H, W, h->ws.capP);
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "map width %d needs %zu B of shared memory per band", W, smem);
     SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_peaks_kernel<<<n * h->ws.K, kNmsThreads, smem, st>>>(a);
@@ -134,7 +137,13 @@ int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
     const bool aligned = (plane_bytes % 16 == 0) && ((a.img_stride * sizeof(T)) % 16 == 0) && ((a.chan_stride * sizeof(T)) % 16 == 0) &&
                          ((reinterpret_cast<uintptr_t>(a.paf) & 15) == 0) && plane_bytes < (1u << 20);
     const int grid = n * h->ws.L;
-    if (aligned && staged <= h->smem_optin) {
+    if (sizeof(T) == 4 && h->persist && aligned && h->ws.capP <= kPersistMaxCapP &&
+        persist_smem_bytes(plane_bytes, h->ws.capP) <= h->smem_optin) {
+        // one resident CTA per SM walking a ring of 3 plane slots (loader / screeners / scorers)
+        const size_t smem = persist_smem_bytes(plane_bytes, h->ws.capP);
+        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limb_score_persist_kernel<<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+    } else if (aligned && staged <= h->smem_optin) {
         SPG_CUDA(h, cudaFuncSetAttribute(limb_score_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
         limb_score_kernel<T, true><<<grid, kScoreThreads, staged, st>>>(a);
     } else {  // plane larger than shared memory (or unaligned): sample through L2
@@ -256,6 +265,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
+    if (const char *e = getenv("SPG_SCORE_PERSIST")) h->persist = !(e[0] == '0');
     DeviceGuard guard(h->device);
 
     const size_t N = cfg->max_batch, K = cfg->n_parts, L = cfg->n_limbs, J = cfg->n_out_joints;
