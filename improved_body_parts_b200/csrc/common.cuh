@@ -98,6 +98,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Same, for waits that can be long (role hand-offs in persistent kernels): back off with NANOSLEEP so that a
+// waiting warp does not take issue slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+    uint32_t ns = 32;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+    }
+}
 
 // numpy's pairwise summation order for 8 <= n <= 128 (and the plain loop for n < 8): what both
 // `score_box.sum()` (f32) and `(score_box * grid).sum()` (f64) use in utils/util.py:206-211.

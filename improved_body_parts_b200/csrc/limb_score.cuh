@@ -285,13 +285,11 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
                     const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
                     if (n2 > 1e-6f) {
                         const float q = n2 * rsqrtf(n2) + 1.0f;  // approximate norm + 1: m is only trusted 0.01 away from a tie
-                        int m = -1;
-                        if (q >= (float)a.mid_num + 0.51f) {
-                            m = a.mid_num;
-                        } else {
-                            const float r = rintf(q);
-                            if (fabsf(q - r) < 0.49f) m = min((int)r, a.mid_num);  // else: m uncertain -> survive
-                        }
+                        // branch-free: lanes with long and short pairs must reach the sample loop together
+                        const float r = rintf(q);
+                        const bool longp = q >= (float)a.mid_num + 0.51f;
+                        int m = longp ? a.mid_num : min((int)r, a.mid_num);
+                        if (!longp && !(fabsf(q - r) < 0.49f)) m = -1;  // m within 0.01 of a rounding tie -> survive
                         if (m >= 1) {
                             const int maxfail = s_maxfail[m];
                             const int qn = s_qn[m];

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
         // =========================== loader ===========================
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots;
-            if (j >= kPersistSlots) mbar_wait(&bar_free[s], ((j / kPersistSlots) - 1) & 1);
+            if (j >= kPersistSlots) mbar_wait_sleep(&bar_free[s], ((j / kPersistSlots) - 1) & 1);
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / L, k = item - n_local * L;
             const int n = a.image_base + n_local;
@@ -185,14 +185,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
         constexpr int kStrideA = kScreenWarps * 32;
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots, q = j & 1;
-            mbar_wait(&bar_full[s], (j / kPersistSlots) & 1);
-            if (j >= 2) mbar_wait(&bar_bdone[q], ((j >> 1) - 1) & 1);
+            mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);
+            if (j >= 2) mbar_wait_sleep(&bar_bdone[q], ((j >> 1) - 1) & 1);
             const PersistHdr h = s_hdr[s];
             const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
             const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
             uint16_t *list = s_list + q * list_stride;
             const int nB = h.nB;
-            for (int base = 0; base < h.npairs; base += kStrideA) {
+            for (int base = 0; base + (tidA & ~31) < h.npairs; base += kStrideA) {  // warps without pairs skip the pass
                 const int p = base + tidA;
                 bool keep = false;
                 if (p < h.npairs) {
@@ -206,13 +206,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                             const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
                             if (n2 > 1e-6f) {
                                 const float qf = n2 * rsqrtf(n2) + 1.0f;  // approximate norm + 1
-                                int m = -1;
-                                if (qf >= (float)a.mid_num + 0.51f) {
-                                    m = a.mid_num;
-                                } else {
-                                    const float r = rintf(qf);
-                                    if (fabsf(qf - r) < 0.49f) m = min((int)r, a.mid_num);  // else uncertain -> survive
-                                }
+                                // branch-free: lanes with long and short pairs must reach the sample loop together
+                                const float r = rintf(qf);
+                                const bool longp = qf >= (float)a.mid_num + 0.51f;
+                                int m = longp ? a.mid_num : min((int)r, a.mid_num);
+                                if (!longp && !(fabsf(qf - r) < 0.49f)) m = -1;  // m within 0.01 of a rounding tie -> survive
                                 if (m >= 1) {
                                     const int maxfail = s_maxfail[m];
                                     const int qn = s_qn[m];
@@ -251,8 +249,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
         constexpr int kStrideB = kScorerWarps * 32;
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots, q = j & 1;
-            mbar_wait(&bar_adone[q], (j >> 1) & 1);
-            mbar_wait(&bar_full[s], (j / kPersistSlots) & 1);  // already complete; makes the plane visible to this warp
+            mbar_wait_sleep(&bar_adone[q], (j >> 1) & 1);
+            mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);  // already complete; makes the plane visible to this warp
             const PersistHdr h = s_hdr[s];
             const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
             const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);

@@ -24,6 +24,7 @@ struct NmsArgs {
 };
 
 constexpr int kNmsThreads = 256;
+constexpr int kNmsBufs = 3;  // band ring: two bands in flight while one is scanned
 
 __device__ __forceinline__ bool nms_is_peak(const float *buf, int lo, int H, int W, int y, int x, float v, float thr) {
     // keep = (hmax == heat) & (heat >= thre); np.nonzero(heat * keep) drops exact zeros
@@ -90,9 +91,9 @@ __device__ __forceinline__ void refine_box(const float *__restrict__ plane, int 
     sc = __fdiv_rn(s32, (float)N);  // score_box.mean() stays f32
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 3) nms_peaks_kernel(NmsArgs a) {
+__global__ void __launch_bounds__(kNmsThreads, 4) nms_peaks_kernel(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar[2];
+    __shared__ uint64_t bar[kNmsBufs];
     __shared__ int s_count;
 
     const Workspace &ws = a.ws;
@@ -106,17 +107,17 @@ __global__ void __launch_bounds__(kNmsThreads, 3) nms_peaks_kernel(NmsArgs a) {
     const int nb = (H + br - 1) / br;
     // one band (whole plane resident): a single buffer without halo rows; else two band buffers with a halo row each side
     const size_t band_floats = nb == 1 ? (size_t)H * W : (size_t)(br + 2) * W;
+    const size_t buf_stride = (band_floats + 31) & ~(size_t)31;
+    const int nbufs = min(nb, kNmsBufs);
     float *buf0 = reinterpret_cast<float *>(smem_raw);
-    float *buf1 = nb == 1 ? buf0 : buf0 + ((band_floats + 31) & ~(size_t)31);
-    uint32_t *s_list = reinterpret_cast<uint32_t *>(buf1 + ((band_floats + 31) & ~(size_t)31));
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(buf0 + (size_t)nbufs * buf_stride);
     uint32_t *s_sorted = s_list + ws.capP;
     uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_sorted + ws.capP);  // float4 groups of the band worth testing
 
     if (tid == 0) {
         s_count = 0;
         if (a.use_bulk) {
-            mbar_init(&bar[0], 1);
-            mbar_init(&bar[1], 1);
+            for (int i = 0; i < kNmsBufs; i++) mbar_init(&bar[i], 1);
             fence_mbar_init();
         }
     }
@@ -124,21 +125,21 @@ __global__ void __launch_bounds__(kNmsThreads, 3) nms_peaks_kernel(NmsArgs a) {
 
     auto band_lo = [&](int b) { return max(b * br - 1, 0); };
     auto band_hi = [&](int b) { return min((b + 1) * br + 1, H); };
-    auto issue = [&](int b) {  // one thread: bulk copy rows [lo, hi) of the plane into buffer b&1
+    auto issue = [&](int b) {  // one thread: bulk copy rows [lo, hi) of the plane into ring buffer b % kNmsBufs
         const int lo = band_lo(b), hi = band_hi(b);
         const uint32_t bytes = (uint32_t)(hi - lo) * W * sizeof(float);
-        mbar_expect_tx(&bar[b & 1], bytes);
-        bulk_g2s((b & 1) ? buf1 : buf0, plane + (size_t)lo * W, bytes, &bar[b & 1]);
+        mbar_expect_tx(&bar[b % kNmsBufs], bytes);
+        bulk_g2s(buf0 + (size_t)(b % kNmsBufs) * buf_stride, plane + (size_t)lo * W, bytes, &bar[b % kNmsBufs]);
     };
 
-    if (a.use_bulk && tid == 0) issue(0);
+    if (a.use_bulk && tid == 0)
+        for (int b = 0; b < nbufs; b++) issue(b);
 
     for (int b = 0; b < nb; b++) {
-        float *buf = (b & 1) ? buf1 : buf0;
+        float *buf = a.use_bulk ? buf0 + (size_t)(b % kNmsBufs) * buf_stride : buf0;
         const int lo = band_lo(b), hi = band_hi(b);
         if (a.use_bulk) {
-            if (tid == 0 && b + 1 < nb) issue(b + 1);  // the other buffer was released by the barrier below
-            mbar_wait(&bar[b & 1], (b >> 1) & 1);
+            mbar_wait(&bar[b % kNmsBufs], (b / kNmsBufs) & 1);
         } else {
             const int cnt = (hi - lo) * W;
             for (int i = tid; i < cnt; i += kNmsThreads) buf[i] = plane[(size_t)lo * W + i];
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(kNmsThreads, 3) nms_peaks_kernel(NmsArgs a) {
             }
         }
         __syncthreads();  // band consumed: its buffer may be refilled, s_count/s_list visible
+        if (a.use_bulk && tid == 0 && b + kNmsBufs < nb) issue(b + kNmsBufs);
     }
 
     const int total = s_count;
@@ -264,7 +266,8 @@ inline size_t nms_smem_bytes(int band_rows, int H, int W, int capP) {
     const bool single = band_rows >= H;
     const size_t band_floats = ((single ? (size_t)H * W : (size_t)(band_rows + 2) * W) + 31) & ~(size_t)31;
     const size_t queue = (((size_t)std::min(band_rows, H) * W / 4 + 8) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    return (single ? 1 : 2) * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t) + queue;
+    const int nb = single ? 1 : (H + band_rows - 1) / band_rows;
+    return (size_t)std::min(nb, kNmsBufs) * band_floats * sizeof(float) + 2 * (size_t)capP * sizeof(uint32_t) + queue;
 }
 
 }  // namespace spg

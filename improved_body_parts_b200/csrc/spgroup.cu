@@ -114,8 +114,8 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.chan_stride = chan_stride;
     a.H = H;
     a.W = W;
-    // whole plane resident when it leaves room for 3 CTAs per SM, else double-buffered bands of ~16 KB
-    a.band_rows = ((size_t)H * W * sizeof(float) <= 72 * 1024) ? H : std::max(4, std::min(H, 4096 / W));
+    // bands of ~16 KB through a ring of 3 buffers: two bands in flight per CTA while one is scanned, 4 CTAs per SM
+    a.band_rows = std::max(4, std::min(H, 4096 / W));
     a.radius = p->offset_radius;
     a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
     a.image_base = base;
