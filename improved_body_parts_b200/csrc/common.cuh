@@ -98,13 +98,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// Same, for waits that can be long (role hand-offs in persistent kernels): back off with NANOSLEEP so that a
-// waiting warp does not take issue slots from the warps it is waiting for.
+// Same, for waits that can be long (role hand-offs in persistent kernels): pass a suspend-time hint so the warp is
+// parked by the hardware instead of polling, and does not take issue slots from the warps it is waiting for.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
-    uint32_t ns = 32;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
     }
 }
 

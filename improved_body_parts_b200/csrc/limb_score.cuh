@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
                         const bool longp = q >= (float)a.mid_num + 0.51f;
                         int m = longp ? a.mid_num : min((int)r, a.mid_num);
                         if (!longp && !(fabsf(q - r) < 0.49f)) m = -1;  // m within 0.01 of a rounding tie -> survive
+                        asm volatile("" : "+r"(m));  // keep ONE copy of the sample loop (no specialisation on m == mid_num)
                         if (m >= 1) {
                             const int maxfail = s_maxfail[m];
                             const int qn = s_qn[m];

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                                 const bool longp = qf >= (float)a.mid_num + 0.51f;
                                 int m = longp ? a.mid_num : min((int)r, a.mid_num);
                                 if (!longp && !(fabsf(qf - r) < 0.49f)) m = -1;  // m within 0.01 of a rounding tie -> survive
+                                asm volatile("" : "+r"(m));  // keep ONE copy of the sample loop (no specialisation on m == mid_num)
                                 if (m >= 1) {
                                     const int maxfail = s_maxfail[m];
                                     const int qn = s_qn[m];
