@@ -35,7 +35,7 @@ namespace spg {
 struct ScoreArgs {
     const void *paf;
     int64_t img_stride, chan_stride;  // elements
-    int H, W, image_base, mid_num, screen;
+    int H, W, image_base, mid_num, screen, debug;  // debug: bench-only knobs of the persistent kernel (0 in production)
     double image_extent, thre2, connect_ration;
     Workspace ws;
 };

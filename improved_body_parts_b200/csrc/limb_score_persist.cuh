@@ -6,15 +6,15 @@
 // issue slots idle at every barrier.  Here one CTA per SM stays resident and walks over its items
 // (item = image * L + limb, strided by the grid) through a ring of 3 plane slots with three roles:
 //
-//   loader   (warp 0)       waits for a free slot, stages the item's two end-point lists (every slot of the
-//                           capacity is fetched, so the loads do not wait for the counters), then issues the
-//                           plane's bulk copy (TMA, SASS UBLKCP) onto the slot's `full` mbarrier.  Runs up to
-//                           two items ahead.
-//   screeners (warps 1-27)  phase A of item j: one thread per pair, survivors appended (warp-aggregated) to one
-//                           of two survivor lists; each warp arrives on `a_done`.
-//   scorers  (warps 28-31)  phase B of item j-1, concurrently with the screeners working on item j: one thread
-//                           per survivor, candidates appended to global memory; the last warp publishes the
-//                           counters, recycles the list and every warp arrives on `b_done` / `slot_free`.
+//   loader   (warp 0)       waits for a free slot, issues the plane's bulk copy (TMA, SASS UBLKCP) onto the slot's
+//                           `full` mbarrier, then publishes the item's two end-point lists, which it fetched into
+//                           registers one item earlier (every slot of the capacity is fetched, so the loads do not
+//                           wait for the counters).  Neither global latency sits on the critical path.
+//   workers  (warps 1-31)   per item j: phase A (screen) of their share of the pairs -- survivors are appended,
+//                           warp-aggregated, to one of two lists -- then they pick up phase B (exact) work of item
+//                           j-1 in chunks of 32 survivors from a shared counter, so whichever warps are ahead do
+//                           the exact evaluation while the others are already screening the next item.  The last
+//                           worker through publishes the item's counters and recycles the list.
 //
 // All hand-offs are mbarriers (no __syncthreads after start-up); the per-m tables are built once per CTA.
 #pragma once
@@ -25,8 +25,7 @@ namespace spg {
 
 constexpr int kPersistThreads = 1024;
 constexpr int kPersistSlots = 3;
-constexpr int kScorerWarps = 4;
-constexpr int kScreenWarps = kPersistThreads / 32 - 1 - kScorerWarps;  // 27
+constexpr int kWorkerWarps = kPersistThreads / 32 - 1;  // 31
 constexpr int kPersistMaxCapP = 64;
 
 struct PersistHdr {
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[kPersistSlots], bar_free[kPersistSlots], bar_adone[2], bar_bdone[2];
     __shared__ PersistHdr s_hdr[kPersistSlots];
-    __shared__ int s_nsurv[2], s_ncand[2], s_done[2];
+    __shared__ int s_nsurv[2], s_ncand[2], s_done[2], s_bnext[2];
     __shared__ uint32_t s_flags[2];
 
     using T = float;
@@ -100,13 +99,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     // ---- one-time set-up
     if (tid == 0) {
         for (int s = 0; s < kPersistSlots; s++) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_free[s], kScorerWarps);
+            mbar_init(&bar_full[s], 2);  // plane copy (expect_tx) + end-point lists
+            mbar_init(&bar_free[s], kWorkerWarps);
         }
         for (int q = 0; q < 2; q++) {
-            mbar_init(&bar_adone[q], kScreenWarps);
-            mbar_init(&bar_bdone[q], kScorerWarps);
-            s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0;
+            mbar_init(&bar_adone[q], kWorkerWarps);
+            mbar_init(&bar_bdone[q], kWorkerWarps);
+            s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0; s_bnext[q] = 0;
         }
         fence_mbar_init();
     }
@@ -133,65 +132,150 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
 
     if (warp == 0) {
         // =========================== loader ===========================
+        // Software-pipelined: the end-point lists of item j+1 are already in registers while item j is published, and
+        // the plane copy is issued before the lists are written, so neither global latency sits on the critical path.
+        constexpr int kMaxE = kPersistMaxCapP / 32;  // list entries per lane
+        double r_xa[kMaxE], r_ya[kMaxE], r_xb[kMaxE], r_yb[kMaxE];
+        float r_sa[kMaxE], r_sb[kMaxE];
+        int r_cntA = 0, r_cntB = 0;
+        auto fetch = [&](int j) {
+            const int item = (int)blockIdx.x + j * G;
+            const int n_local = item / L, k = item - n_local * L;
+            const int n = a.image_base + n_local;
+            const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
+            r_cntA = ws.peak_count[(size_t)n * ws.K + pa];
+            r_cntB = ws.peak_count[(size_t)n * ws.K + pb];
+            const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
+#pragma unroll
+            for (int u = 0; u < kMaxE; u++) {
+                const int e = lane + 32 * u;
+                if (e < capP) {  // whole capacity: independent of the counters
+                    r_xa[u] = ws.peak_x[baseA + e]; r_ya[u] = ws.peak_y[baseA + e];
+                    r_xb[u] = ws.peak_x[baseB + e]; r_yb[u] = ws.peak_y[baseB + e];
+                    r_sa[u] = ws.peak_score[baseA + e]; r_sb[u] = ws.peak_score[baseB + e];
+                }
+            }
+        };
+        if (nj > 0) fetch(0);
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots;
             if (j >= kPersistSlots) mbar_wait_sleep(&bar_free[s], ((j / kPersistSlots) - 1) & 1);
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / L, k = item - n_local * L;
             const int n = a.image_base + n_local;
-            const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
-            const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
-            const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
-            PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
-            for (int e = lane; e < capP; e += 32) {  // whole capacity: independent of the counters
-                const double xa = ws.peak_x[baseA + e], ya = ws.peak_y[baseA + e];
-                const double xb = ws.peak_x[baseB + e], yb = ws.peak_y[baseB + e];
-                const float sa = ws.peak_score[baseA + e], sb = ws.peak_score[baseB + e];
-                ps.ax[e] = xa; ps.ay[e] = ya; ps.bx[e] = xb; ps.by[e] = yb;
-                ps.as[e] = sa; ps.bs[e] = sb;
-                ps.fax[e] = (float)(xa * 64.0); ps.fay[e] = (float)(ya * 64.0);
-                ps.fbx[e] = (float)(xb * 64.0); ps.fby[e] = (float)(yb * 64.0);
-                ps.ain[e] = xa >= 1.0 && xa <= (double)(W - 2) && ya >= 1.0 && ya <= (double)(H - 2);
-                ps.bin[e] = xb >= 1.0 && xb <= (double)(W - 2) && yb >= 1.0 && yb <= (double)(H - 2);
+            if (lane == 0) {  // plane first (arrival 1 of 2 on `full`, carries the byte count)
+                const unsigned char *gplane = reinterpret_cast<const unsigned char *>(
+                    reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride);
+                unsigned char *dst = smem_raw + s * plane_stride;
+                mbar_expect_tx(&bar_full[s], (uint32_t)plane_bytes);
+                for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
+                    const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
+                    bulk_g2s(dst + off, gplane + off, bytes, &bar_full[s]);
+                }
             }
-            const int nA = min(cntA, capP), nB = min(cntB, capP);
+            PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
+#pragma unroll
+            for (int u = 0; u < kMaxE; u++) {
+                const int e = lane + 32 * u;
+                if (e < capP) {
+                    const double xa = r_xa[u], ya = r_ya[u], xb = r_xb[u], yb = r_yb[u];
+                    ps.ax[e] = xa; ps.ay[e] = ya; ps.bx[e] = xb; ps.by[e] = yb;
+                    ps.as[e] = r_sa[u]; ps.bs[e] = r_sb[u];
+                    ps.fax[e] = (float)(xa * 64.0); ps.fay[e] = (float)(ya * 64.0);
+                    ps.fbx[e] = (float)(xb * 64.0); ps.fby[e] = (float)(yb * 64.0);
+                    ps.ain[e] = xa >= 1.0 && xa <= (double)(W - 2) && ya >= 1.0 && ya <= (double)(H - 2);
+                    ps.bin[e] = xb >= 1.0 && xb <= (double)(W - 2) && yb >= 1.0 && yb <= (double)(H - 2);
+                }
+            }
+            const int nA = min(r_cntA, capP), nB = min(r_cntB, capP);
             const bool special = nA == 0 || nB == 0;
             if (lane == 0) {
                 PersistHdr h;
-                h.nA = nA; h.nB = nB; h.npairs = special ? 0 : nA * nB; h.n = n; h.k = k; h.special = special;
+                h.nA = nA; h.nB = nB; h.npairs = (special || a.debug == 1) ? 0 : nA * nB; h.n = n; h.k = k; h.special = special;
                 h.magic = nB > 1 ? 0xffffffffu / (uint32_t)nB + 1u : 0u;
                 h.pad = 0;
                 s_hdr[s] = h;
             }
             __syncwarp();
-            if (lane == 0) {
-                if (special) {
-                    mbar_arrive(&bar_full[s]);
-                } else {
-                    const unsigned char *gplane = reinterpret_cast<const unsigned char *>(
-                        reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride);
-                    unsigned char *dst = smem_raw + s * plane_stride;
-                    mbar_expect_tx(&bar_full[s], (uint32_t)plane_bytes);
-                    for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
-                        const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
-                        bulk_g2s(dst + off, gplane + off, bytes, &bar_full[s]);
+            if (lane == 0) mbar_arrive(&bar_full[s]);  // arrival 2 of 2: lists + header are in place
+            if (j + 1 < nj) fetch(j + 1);              // in flight while the next iteration waits for its slot
+        }
+    } else {
+        // =========================== workers ===========================
+        const int tidA = tid - 32;
+        constexpr int kStrideA = kWorkerWarps * 32;
+
+        // phase B of item jb: exact evaluation of survivor chunks taken from a shared counter; every worker passes
+        // through here exactly once per item and arrives on b_done / slot_free when it has finished what it took
+        auto phase_b = [&](int jb) {
+            const int s = jb % kPersistSlots, q = jb & 1;
+            mbar_wait_sleep(&bar_adone[q], (jb >> 1) & 1);  // all workers have screened item jb: the list is complete
+            const PersistHdr h = s_hdr[s];
+            const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
+            const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
+            const uint16_t *list = s_list + q * list_stride;
+            const int ns = a.debug == 2 ? 0 : s_nsurv[q];
+            const int nB = h.nB;
+            const size_t slot = (size_t)h.n * L + h.k;
+            const size_t out_base = slot * ws.capC;
+            PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
+            for (;;) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_bnext[q], 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                const int t = c * 32 + lane;
+                if (c * 32 >= ns) break;
+                if (t < ns) {
+                    const int p = list[t];
+                    const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
+                    const int jj = p - i * nB;
+                    double score, prio;
+                    bool bad = false;
+                    const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
+                    if (bad) atomicOr(&s_flags[q], kStSampleIndex);
+                    if (ok) {
+                        const int pos = atomicAdd(&s_ncand[q], 1);
+                        if (pos < ws.capC) {
+                            const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)jj;
+                            ws.cand_prio[out_base + pos] = prio;
+                            ws.cand_score[out_base + pos] = score;
+                            ws.cand_ij[out_base + pos] = ij;
+                            const uint32_t b = __float_as_uint((float)prio);
+                            const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                            ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                        }
                     }
                 }
+                __syncwarp();
             }
-        }
-    } else if (warp <= kScreenWarps) {
-        // =========================== screeners (phase A) ===========================
-        const int tidA = tid - 32;
-        constexpr int kStrideA = kScreenWarps * 32;
+            if (lane == 0) {
+                __threadfence_block();  // this warp's appends before its "done" tick (and the other warps' after it)
+                const bool last = atomicAdd(&s_done[q], 1) == kWorkerWarps - 1;
+                __threadfence_block();
+                if (last) {  // last worker through: publish + recycle
+                    const int total = s_ncand[q];
+                    ws.cand_count[slot] = h.special ? -1 : min(total, ws.capC);
+                    if (ws.surv_count) ws.surv_count[slot] = ns;
+                    uint32_t f = s_flags[q];
+                    if (total > ws.capC) f |= kStCandOverflow;
+                    if (f) atomicOr(&ws.status[h.n], f);
+                    s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0; s_bnext[q] = 0;
+                }
+                mbar_arrive(&bar_bdone[q]);
+                mbar_arrive(&bar_free[s]);
+            }
+        };
+
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots, q = j & 1;
             mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);
-            if (j >= 2) mbar_wait_sleep(&bar_bdone[q], ((j >> 1) - 1) & 1);
+            if (j >= 2) mbar_wait_sleep(&bar_bdone[q], ((j >> 1) - 1) & 1);  // list q recycled (item j-2 fully done)
             const PersistHdr h = s_hdr[s];
             const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
             const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
             uint16_t *list = s_list + q * list_stride;
             const int nB = h.nB;
+            // ---- phase A (screen) of item j
             for (int base = 0; base + (tidA & ~31) < h.npairs; base += kStrideA) {  // warps without pairs skip the pass
                 const int p = base + tidA;
                 bool keep = false;
@@ -217,15 +301,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                                     const int qn = s_qn[m];
                                     const float inv = s_inv64[m];
                                     const float sx64 = dx64 * inv, sy64 = dy64 * inv;
+                                    // +33 folded into the start point: with u = pos + 33 (1/64 px), the pixel is u >> 6 for every
+                                    // sample that is not within {31,32,33} (mod 64) of a rounding boundary, i.e. u & 63 > 2
+                                    const float ax64o = ax64 + 33.0f, ay64o = ay64 + 33.0f;
                                     const float *ts = s_ts + m * kScreenSamples;
                                     int fails = 0;
                                     for (int q2 = 0; q2 < qn; q2++) {
                                         const float tf = ts[q2];
-                                        const int xs = __float2int_rn(__fmaf_rn(tf, sx64, ax64));
-                                        const int ys = __float2int_rn(__fmaf_rn(tf, sy64, ay64));
-                                        const unsigned cx = (unsigned)(xs + 33) & 63u, cy = (unsigned)(ys + 33) & 63u;
-                                        const T v = plane[((ys + 32) >> 6) * W + ((xs + 32) >> 6)];
-                                        fails += (min(cx, cy) > 2u) && !(v > thre2);
+                                        const int xu = __float2int_rn(__fmaf_rn(tf, sx64, ax64o));
+                                        const int yu = __float2int_rn(__fmaf_rn(tf, sy64, ay64o));
+                                        const T v = plane[(yu >> 6) * W + (xu >> 6)];
+                                        fails += (((unsigned)xu & 63u) > 2u) && (((unsigned)yu & 63u) > 2u) && !(v > thre2);
                                     }
                                     keep = fails <= maxfail;
                                 }
@@ -243,63 +329,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_adone[q]);
+            // ---- phase B (exact) work of the previous item, for whichever warps get here while chunks are left
+            if (j >= 1) phase_b(j - 1);
         }
-    } else {
-        // =========================== scorers (phase B) ===========================
-        const int tidB = tid - (kScreenWarps + 1) * 32;
-        constexpr int kStrideB = kScorerWarps * 32;
-        for (int j = 0; j < nj; j++) {
-            const int s = j % kPersistSlots, q = j & 1;
-            mbar_wait_sleep(&bar_adone[q], (j >> 1) & 1);
-            mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);  // already complete; makes the plane visible to this warp
-            const PersistHdr h = s_hdr[s];
-            const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
-            const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
-            const uint16_t *list = s_list + q * list_stride;
-            const int ns = s_nsurv[q];
-            const int nB = h.nB;
-            const size_t slot = (size_t)h.n * L + h.k;
-            const size_t out_base = slot * ws.capC;
-            PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
-            for (int t = tidB; t < ns; t += kStrideB) {
-                const int p = list[t];
-                const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
-                const int jj = p - i * nB;
-                double score, prio;
-                bool bad = false;
-                const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
-                if (bad) atomicOr(&s_flags[q], kStSampleIndex);
-                if (ok) {
-                    const int pos = atomicAdd(&s_ncand[q], 1);
-                    if (pos < ws.capC) {
-                        const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)jj;
-                        ws.cand_prio[out_base + pos] = prio;
-                        ws.cand_score[out_base + pos] = score;
-                        ws.cand_ij[out_base + pos] = ij;
-                        const uint32_t b = __float_as_uint((float)prio);
-                        const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                        ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();  // this warp's candidate appends before its "done" tick (and the other warps' after it)
-                const bool last = atomicAdd(&s_done[q], 1) == kScorerWarps - 1;
-                __threadfence_block();
-                if (last) {  // last scorer warp of this item: publish + recycle
-                    const int total = s_ncand[q];
-                    ws.cand_count[slot] = h.special ? -1 : min(total, ws.capC);
-                    if (ws.surv_count) ws.surv_count[slot] = ns;
-                    uint32_t f = s_flags[q];
-                    if (total > ws.capC) f |= kStCandOverflow;
-                    if (f) atomicOr(&ws.status[h.n], f);
-                    s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0;
-                }
-                mbar_arrive(&bar_bdone[q]);
-                mbar_arrive(&bar_free[s]);
-            }
-        }
+        if (nj >= 1) phase_b(nj - 1);
     }
 }
 
