@@ -27,6 +27,7 @@ constexpr int kPersistThreads = 1024;
 constexpr int kPersistSlots = 3;
 constexpr int kWorkerWarps = kPersistThreads / 32 - 1;  // 31
 constexpr int kPersistMaxCapP = 64;
+constexpr int kPersistListCap = 2048;  // survivors queued per item; the (rare) excess is evaluated inline by the screener
 
 struct PersistHdr {
     int nA, nB, npairs, n, k, special;
@@ -43,7 +44,7 @@ __host__ __device__ inline size_t persist_tables_bytes() {
 inline size_t persist_smem_bytes(size_t plane_bytes, int capP) {
     const size_t plane = (plane_bytes + 127) & ~(size_t)127;
     return kPersistSlots * plane + kPersistSlots * persist_peaks_bytes(capP) + persist_tables_bytes() +
-           2 * (size_t)capP * capP * sizeof(uint16_t) + 256;
+           kPersistSlots * (size_t)kPersistListCap * sizeof(uint16_t) + 256;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -74,10 +75,10 @@ __device__ __forceinline__ PeakSlot peak_slot(unsigned char *base, int capP) {
 
 __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar_full[kPersistSlots], bar_free[kPersistSlots], bar_adone[2], bar_bdone[2];
+    __shared__ uint64_t bar_full[kPersistSlots], bar_free[kPersistSlots], bar_adone[kPersistSlots];
     __shared__ PersistHdr s_hdr[kPersistSlots];
-    __shared__ int s_nsurv[2], s_ncand[2], s_done[2], s_bnext[2];
-    __shared__ uint32_t s_flags[2];
+    __shared__ int s_nsurv[kPersistSlots], s_ncand[kPersistSlots], s_done[kPersistSlots], s_bnext[kPersistSlots];
+    __shared__ uint32_t s_flags[kPersistSlots];
 
     using T = float;
     const Workspace &ws = a.ws;
@@ -93,19 +94,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     float *s_inv64 = s_ts + (size_t)(kScreenMaxMid + 1) * kScreenSamples;
     signed char *s_maxfail = reinterpret_cast<signed char *>(s_inv64 + (kScreenMaxMid + 1));
     unsigned char *s_qn = reinterpret_cast<unsigned char *>(s_maxfail + (kScreenMaxMid + 1));
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(tables + persist_tables_bytes());  // [2][capP*capP]
-    const int list_stride = capP * capP;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(tables + persist_tables_bytes());  // [slots][kPersistListCap]
+    const int list_stride = kPersistListCap;
 
     // ---- one-time set-up
     if (tid == 0) {
         for (int s = 0; s < kPersistSlots; s++) {
             mbar_init(&bar_full[s], 2);  // plane copy (expect_tx) + end-point lists
             mbar_init(&bar_free[s], kWorkerWarps);
-        }
-        for (int q = 0; q < 2; q++) {
-            mbar_init(&bar_adone[q], kWorkerWarps);
-            mbar_init(&bar_bdone[q], kWorkerWarps);
-            s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0; s_bnext[q] = 0;
+            mbar_init(&bar_adone[s], kWorkerWarps);
+            s_nsurv[s] = 0; s_ncand[s] = 0; s_done[s] = 0; s_flags[s] = 0; s_bnext[s] = 0;
         }
         fence_mbar_init();
     }
@@ -207,45 +205,48 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
 
         // phase B of item jb: exact evaluation of survivor chunks taken from a shared counter; every worker passes
         // through here exactly once per item and arrives on b_done / slot_free when it has finished what it took
+        // exact evaluation of one pair of the item in slot s + candidate append (phase B; also the inline path of a
+        // screener whose survivor does not fit the list)
+        auto exact_one = [&](int s, const PersistHdr &h, const PeakSlot &ps, const T *plane, int p) {
+            const int nB = h.nB;
+            const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
+            const int jj = p - i * nB;
+            PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
+            double score, prio;
+            bool bad = false;
+            const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
+            if (bad) atomicOr(&s_flags[s], kStSampleIndex);
+            if (ok) {
+                const size_t out_base = ((size_t)h.n * L + h.k) * ws.capC;
+                const int pos = atomicAdd(&s_ncand[s], 1);
+                if (pos < ws.capC) {
+                    const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)jj;
+                    ws.cand_prio[out_base + pos] = prio;
+                    ws.cand_score[out_base + pos] = score;
+                    ws.cand_ij[out_base + pos] = ij;
+                    const uint32_t b = __float_as_uint((float)prio);
+                    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                    ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                }
+            }
+        };
+
         auto phase_b = [&](int jb) {
-            const int s = jb % kPersistSlots, q = jb & 1;
-            mbar_wait_sleep(&bar_adone[q], (jb >> 1) & 1);  // all workers have screened item jb: the list is complete
+            const int s = jb % kPersistSlots, q = s;  // list and counters live with the plane slot
+            mbar_wait_sleep(&bar_adone[q], (jb / kPersistSlots) & 1);  // all workers have screened item jb: the list is complete
             const PersistHdr h = s_hdr[s];
             const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
             const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
             const uint16_t *list = s_list + q * list_stride;
-            const int ns = a.debug == 2 ? 0 : s_nsurv[q];
-            const int nB = h.nB;
+            const int ns = a.debug == 2 ? 0 : min(s_nsurv[q], kPersistListCap);
             const size_t slot = (size_t)h.n * L + h.k;
-            const size_t out_base = slot * ws.capC;
-            PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
             for (;;) {
                 int c = 0;
                 if (lane == 0) c = atomicAdd(&s_bnext[q], 1);
                 c = __shfl_sync(0xffffffffu, c, 0);
                 const int t = c * 32 + lane;
                 if (c * 32 >= ns) break;
-                if (t < ns) {
-                    const int p = list[t];
-                    const int i = nB > 1 ? (int)__umulhi((uint32_t)p, h.magic) : p;
-                    const int jj = p - i * nB;
-                    double score, prio;
-                    bool bad = false;
-                    const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
-                    if (bad) atomicOr(&s_flags[q], kStSampleIndex);
-                    if (ok) {
-                        const int pos = atomicAdd(&s_ncand[q], 1);
-                        if (pos < ws.capC) {
-                            const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)jj;
-                            ws.cand_prio[out_base + pos] = prio;
-                            ws.cand_score[out_base + pos] = score;
-                            ws.cand_ij[out_base + pos] = ij;
-                            const uint32_t b = __float_as_uint((float)prio);
-                            const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                            ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
-                        }
-                    }
-                }
+                if (t < ns) exact_one(s, h, ps, plane, list[t]);
                 __syncwarp();
             }
             if (lane == 0) {
@@ -255,21 +256,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 if (last) {  // last worker through: publish + recycle
                     const int total = s_ncand[q];
                     ws.cand_count[slot] = h.special ? -1 : min(total, ws.capC);
-                    if (ws.surv_count) ws.surv_count[slot] = ns;
+                    if (ws.surv_count) ws.surv_count[slot] = s_nsurv[q];
                     uint32_t f = s_flags[q];
                     if (total > ws.capC) f |= kStCandOverflow;
                     if (f) atomicOr(&ws.status[h.n], f);
                     s_nsurv[q] = 0; s_ncand[q] = 0; s_done[q] = 0; s_flags[q] = 0; s_bnext[q] = 0;
                 }
-                mbar_arrive(&bar_bdone[q]);
-                mbar_arrive(&bar_free[s]);
+                mbar_arrive(&bar_free[s]);  // slot, list and counters may be reused once every worker has been here
             }
         };
 
         for (int j = 0; j < nj; j++) {
-            const int s = j % kPersistSlots, q = j & 1;
+            const int s = j % kPersistSlots, q = s;
+            // `full` also means the slot's list and counters are recycled: the loader refilled the slot only after every
+            // worker had finished phase B of item j-3
             mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);
-            if (j >= 2) mbar_wait_sleep(&bar_bdone[q], ((j >> 1) - 1) & 1);  // list q recycled (item j-2 fully done)
             const PersistHdr h = s_hdr[s];
             const PeakSlot ps = peak_slot(peaks_base + s * peaks_stride, capP);
             const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
@@ -324,7 +325,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                     int at = 0;
                     if (lane == 0) at = atomicAdd(&s_nsurv[q], __popc(km));
                     at = __shfl_sync(0xffffffffu, at, 0);
-                    if (keep) list[at + __popc(km & ((1u << lane) - 1u))] = (uint16_t)p;
+                    if (keep) {
+                        const int at_me = at + __popc(km & ((1u << lane) - 1u));
+                        if (at_me < kPersistListCap) list[at_me] = (uint16_t)p;
+                        else exact_one(s, h, ps, plane, p);  // list full: evaluate right here
+                    }
                 }
             }
             __syncwarp();
