@@ -27,7 +27,8 @@ struct MatchArgs {
 };
 
 constexpr int kMatchThreads = 128;
-constexpr int kMatchRegCands = 8;  // survivors cached per lane (x32 lanes)
+constexpr int kMatchRegF64 = 8;     // f64-plane path: (key, tie) pairs cached per lane
+constexpr int kMatchRegCands = 16;  // survivor keys cached per lane (x32 lanes = 512 per limb)
 
 __device__ __forceinline__ bool key_better(double pa, int ia, double pb, int ib) {
     return pa > pb || (pa == pb && ia < ib);
@@ -44,15 +45,10 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
 // and score are stored by the lane that owns the winner; limb lengths are filled in afterwards in parallel.
 template <int NS>
 __device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsigned long long (&key8)[kMatchRegCands],
-                                                 const double (&sc8)[kMatchRegCands], size_t obase, int nC, int lim, int lane) {
+                                                 size_t obase, int nC, int lim, int lane) {
     unsigned long long key[NS];  // 0 = dead / absent
-    double sc[NS];
 #pragma unroll
-    for (int r = 0; r < NS; r++) {
-        const bool ok = lane + 32 * r < nC;  // the registers were loaded speculatively, before nC was known
-        key[r] = ok ? key8[r] : 0ull;
-        sc[r] = sc8[r];
-    }
+    for (int r = 0; r < NS; r++) key[r] = (lane + 32 * r < nC) ? key8[r] : 0ull;  // loaded speculatively, before nC was known
     int m = 0;
     while (m < lim) {
         unsigned long long best = key[0];
@@ -64,12 +60,12 @@ __device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsi
         const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
         const uint32_t wij = ~mlo;  // winner's (i << 16) | j; (i, j) pairs are unique, so exactly one lane owns it
         if (hi == mhi && lo == mlo) {
-            double wsc = sc[0];
+            int wr = 0;
 #pragma unroll
             for (int r = 1; r < NS; r++)
-                if (key[r] == best) wsc = sc[r];
-            ws.conn_ij[obase + m] = wij;      // row [idA, idB, score, i, j, norm] (evaluate.py:267)
-            ws.conn_score[obase + m] = wsc;
+                if (key[r] == best) wr = r;
+            ws.conn_ij[obase + m] = wij;  // row [idA, idB, score, i, j, norm] (evaluate.py:267); score and norm follow below
+            reinterpret_cast<int *>(ws.conn_norm + obase + m)[0] = lane + 32 * wr;  // candidate index, replaced by the norm
         }
         // strike everything that shares an end point with the winner (including the winner itself)
 #pragma unroll
@@ -95,13 +91,10 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
     // One round trip to L2 instead of three: the survivor keys/scores are fetched speculatively (any slot below capC
     // is valid memory; slots >= nC are masked later) together with the three counters they would otherwise wait for.
     unsigned long long key8[kMatchRegCands];
-    double sc8[kMatchRegCands];
 #pragma unroll
     for (int r = 0; r < kMatchRegCands; r++) {
         const int cidx = lane + 32 * r;
-        const bool in = a.keys_valid && cidx < ws.capC;
-        key8[r] = in ? ws.cand_key[cbase + cidx] : 0ull;
-        sc8[r] = in ? ws.cand_score[cbase + cidx] : 0.0;
+        key8[r] = (a.keys_valid && cidx < ws.capC) ? ws.cand_key[cbase + cidx] : 0ull;
     }
     const int nC = ws.cand_count[slot];
     const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
@@ -130,29 +123,33 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
         // ---- fast path, f32 planes: one 64-bit key per survivor, all in registers -----------------------
         switch (nslots) {
             case 0: break;
-            case 1: m = match_rounds_keys<1>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 2: m = match_rounds_keys<2>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 3: m = match_rounds_keys<3>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 4: m = match_rounds_keys<4>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 5: m = match_rounds_keys<5>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 6: m = match_rounds_keys<6>(ws, key8, sc8, obase, nC, lim, lane); break;
-            case 7: m = match_rounds_keys<7>(ws, key8, sc8, obase, nC, lim, lane); break;
-            default: m = match_rounds_keys<8>(ws, key8, sc8, obase, nC, lim, lane); break;
+            case 1: m = match_rounds_keys<1>(ws, key8, obase, nC, lim, lane); break;
+            case 2: m = match_rounds_keys<2>(ws, key8, obase, nC, lim, lane); break;
+            case 3: m = match_rounds_keys<3>(ws, key8, obase, nC, lim, lane); break;
+            case 4: m = match_rounds_keys<4>(ws, key8, obase, nC, lim, lane); break;
+            case 5: m = match_rounds_keys<5>(ws, key8, obase, nC, lim, lane); break;
+            case 6: m = match_rounds_keys<6>(ws, key8, obase, nC, lim, lane); break;
+            case 7: m = match_rounds_keys<7>(ws, key8, obase, nC, lim, lane); break;
+            case 8: m = match_rounds_keys<8>(ws, key8, obase, nC, lim, lane); break;
+            case 9: case 10: m = match_rounds_keys<10>(ws, key8, obase, nC, lim, lane); break;
+            case 11: case 12: m = match_rounds_keys<12>(ws, key8, obase, nC, lim, lane); break;
+            default: m = match_rounds_keys<16>(ws, key8, obase, nC, lim, lane); break;
         }
         __syncwarp();  // the rows were written by different lanes of this warp
-        for (int c = lane; c < m; c += 32) {  // limb lengths (the reference's `norm`, :225) in parallel
+        for (int c = lane; c < m; c += 32) {  // scores and limb lengths (the reference's `norm`, :225) in parallel
             const uint32_t ij = ws.conn_ij[obase + c];
+            ws.conn_score[obase + c] = ws.cand_score[cbase + reinterpret_cast<const int *>(ws.conn_norm + obase + c)[0]];
             const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
             const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
             const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
             ws.conn_norm[obase + c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
         }
-    } else if (nC <= 32 * kMatchRegCands) {
+    } else if (nC <= 32 * kMatchRegF64) {
         // ---- register path, f64 planes: (ordered f64 priority, tie-break) -------------------------------
-        unsigned long long r_key[kMatchRegCands];  // ordered priority bits; 0 = dead / absent
-        uint32_t r_tie[kMatchRegCands];            // ~((i << 16) | j): larger = earlier in generation order
+        unsigned long long r_key[kMatchRegF64];  // ordered priority bits; 0 = dead / absent
+        uint32_t r_tie[kMatchRegF64];            // ~((i << 16) | j): larger = earlier in generation order
 #pragma unroll
-        for (int r = 0; r < kMatchRegCands; r++) {
+        for (int r = 0; r < kMatchRegF64; r++) {
             const int cidx = lane + 32 * r;
             const bool ok = cidx < nC;
             r_key[r] = ok ? ordered_bits(ws.cand_prio[cbase + cidx]) : 0ull;
@@ -163,7 +160,7 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
             uint32_t bt = 0u;
             int br = -1;
 #pragma unroll
-            for (int r = 0; r < kMatchRegCands; r++) {
+            for (int r = 0; r < kMatchRegF64; r++) {
                 const bool better = r_key[r] > bk || (r_key[r] == bk && r_key[r] != 0ull && r_tie[r] > bt);
                 if (better) { bk = r_key[r]; bt = r_tie[r]; br = r; }
             }
@@ -176,7 +173,7 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
             const uint32_t wij = ~mt;
             if (tied && bt == mt) emit(m, wij, lane + 32 * br);
 #pragma unroll
-            for (int r = 0; r < kMatchRegCands; r++) {
+            for (int r = 0; r < kMatchRegF64; r++) {
                 const uint32_t x = ~r_tie[r] ^ wij;
                 if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
             }
