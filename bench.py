@@ -315,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
         hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    names = ["nms_peaks_kernel", "limb_score_kernel<float,true>", "limb_match_kernel", "assemble_kernel"]
+    names = list(g.stage_kernels())  # the kernel variants that actually ran (ncu names)
     alg_bytes = [B * 18 * H * W * 4, B * 30 * H * W * 4, None, None]  # K1 reads heat once, K2a reads paf once
     kernels = {}
     for i, nme in enumerate(names):

@@ -54,7 +54,7 @@ __device__ __forceinline__ void refine_box(const float *__restrict__ plane, int 
                                            float &sc) {
     constexpr int D = 2 * R + 1, N = D * D;
     if (N == 1) {  // radius 0: offsets are 0/b, the mean is the value itself
-        const float b = __ldg(plane + (size_t)y * W + x);
+        const float b = plane[(size_t)y * W + x];
         const float s32 = 0.0f + b;
         rx = __dadd_rn((double)x, __ddiv_rn(__dmul_rn((double)b, 0.0), (double)s32));
         ry = __dadd_rn((double)y, __ddiv_rn(__dmul_rn((double)b, 0.0), (double)s32));
@@ -68,7 +68,7 @@ __device__ __forceinline__ void refine_box(const float *__restrict__ plane, int 
 #pragma unroll
     for (int i = 0; i < N; i++) {
         const int r = i / D - R, q = i % D - R;
-        const float b = __ldg(plane + (size_t)(y + r) * W + (x + q));
+        const float b = plane[(size_t)(y + r) * W + (x + q)];  // global (L2-hot) or shared memory
         const double wr = __dmul_rn((double)b, (double)r), wc = __dmul_rn((double)b, (double)q);
         if (i < 8) {
             s[i] = b; ax[i] = wr; ay[i] = wc;

@@ -23,6 +23,7 @@
 #include "limb_score.cuh"
 #include "limb_score_persist.cuh"
 #include "nms_peaks.cuh"
+#include "nms_peaks_persist.cuh"
 
 using namespace spg;
 
@@ -42,6 +43,7 @@ struct spg_handle {
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
+    const char *stage_kernel[4] = {"", "", "", ""};
     int persist = 1;  // persistent warp-specialised limb_score when it applies (SPG_SCORE_PERSIST=0 turns it off)
     int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
@@ -121,10 +123,23 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.image_base = base;
     a.thr = (float)p->thre1;
     a.ws = h->ws;
+    if (h->persist && a.use_bulk && nms_persist_smem_bytes(H, W, h->ws.capP) <= h->smem_optin && (size_t)H * W / 4 < 65536 &&
+        (size_t)H * W * sizeof(float) < (1u << 20)) {
+        // one resident CTA per SM walking a ring of 3 plane slots (loader + 31 workers)
+        const size_t psm = nms_persist_smem_bytes(H, W, h->ws.capP);
+        const int items = n * h->ws.K;
+        SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        nms_peaks_persist_kernel<<<std::min(items, h->sm_count), kNmsPersistThreads, psm, st>>>(a, items);
+        h->stage_kernel[0] = "nms_peaks_persist_kernel";
+        h->launches++;
+        SPG_CUDA(h, cudaGetLastError());
+        return SPG_OK;
+    }
     const size_t smem = nms_smem_bytes(a.band_rows, H, W, h->ws.capP);
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "map width %d needs %zu B of shared memory per band", W, smem);
     SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_peaks_kernel<<<n * h->ws.K, kNmsThreads, smem, st>>>(a);
+    h->stage_kernel[0] = "nms_peaks_kernel";
     h->launches++;
     SPG_CUDA(h, cudaGetLastError());
     return SPG_OK;
@@ -143,12 +158,15 @@ int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
         const size_t smem = persist_smem_bytes(plane_bytes, h->ws.capP);
         SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         limb_score_persist_kernel<<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+        h->stage_kernel[1] = "limb_score_persist_kernel";
     } else if (aligned && staged <= h->smem_optin) {
         SPG_CUDA(h, cudaFuncSetAttribute(limb_score_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
         limb_score_kernel<T, true><<<grid, kScoreThreads, staged, st>>>(a);
+        h->stage_kernel[1] = sizeof(T) == 4 ? "limb_score_kernel<float,true>" : "limb_score_kernel<double,true>";
     } else {  // plane larger than shared memory (or unaligned): sample through L2
         const size_t smem = score_smem_bytes(0, h->ws.capP);
         limb_score_kernel<T, false><<<grid, kScoreThreads, smem, st>>>(a);
+        h->stage_kernel[1] = sizeof(T) == 4 ? "limb_score_kernel<float,false>" : "limb_score_kernel<double,false>";
     }
     h->launches++;
     SPG_CUDA(h, cudaGetLastError());
@@ -187,6 +205,7 @@ int launch_match(spg_handle *h, int base, int n, cudaStream_t st) {
     const int warps = n * h->ws.L;
     const int blocks = (warps * 32 + kMatchThreads - 1) / kMatchThreads;
     limb_match_kernel<<<blocks, kMatchThreads, 0, st>>>(a);
+    h->stage_kernel[2] = "limb_match_kernel";
     h->launches++;
     SPG_CUDA(h, cudaGetLastError());
     return SPG_OK;
@@ -208,6 +227,7 @@ int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStr
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "capacities need %zu B of shared memory in assemble (limit %zu)", smem, h->smem_optin);
     SPG_CUDA(h, cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     assemble_kernel<<<n, kAssembleThreads, smem, st>>>(a);
+    h->stage_kernel[3] = "assemble_kernel";
     h->launches++;
     SPG_CUDA(h, cudaGetLastError());
     return SPG_OK;
@@ -339,6 +359,8 @@ int spg_get_device_view(const spg_handle *h, spg_device_view *v) {
 }
 
 int64_t spg_launch_count(const spg_handle *h) { return h ? h->launches : 0; }
+
+const char *spg_stage_kernel(const spg_handle *h, int32_t stage) { return (h && stage >= 0 && stage < 4) ? h->stage_kernel[stage] : ""; }
 
 // ---- stages ------------------------------------------------------------------------------------
 int spg_nms_peaks(spg_handle *h, const float *heat, int64_t image_stride, int64_t chan_stride, int32_t n, int32_t H, int32_t W,

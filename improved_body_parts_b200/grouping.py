@@ -28,7 +28,7 @@ EXPORTS = (
     "spg_create", "spg_destroy", "spg_last_error", "spg_abi_version", "spg_get_device_view", "spg_group_batch",
     "spg_group_host", "spg_host_alloc", "spg_host_free", "spg_nms_peaks", "spg_limb_score", "spg_limb_match",
     "spg_assemble", "spg_upload_peaks", "spg_upload_connections", "spg_download_peaks", "spg_download_connections",
-    "spg_download_people", "spg_download_status", "spg_launch_count")
+    "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel")
 
 
 class GroupingError(RuntimeError):
@@ -72,6 +72,8 @@ def load_library() -> C.CDLL:
         lib.spg_last_error.argtypes = [C.c_void_p]
         lib.spg_launch_count.restype = C.c_int64
         lib.spg_launch_count.argtypes = [C.c_void_p]
+        lib.spg_stage_kernel.restype = C.c_char_p
+        lib.spg_stage_kernel.argtypes = [C.c_void_p, C.c_int32]
         lib.spg_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
         lib.spg_destroy.argtypes = [C.c_void_p]
         lib.spg_destroy.restype = None
@@ -225,6 +227,10 @@ class Grouper:
     @property
     def launch_count(self) -> int:
         return int(self._lib.spg_launch_count(self._h))
+
+    def stage_kernels(self):
+        """Names of the kernel variants the last launches used: (nms_peaks, limb_score, limb_match, assemble)."""
+        return tuple((self._lib.spg_stage_kernel(self._h, i) or b"").decode() for i in range(4))
 
     # -- helpers ---------------------------------------------------------------------------------
     @staticmethod

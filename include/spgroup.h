@@ -162,6 +162,9 @@ int spg_download_status(spg_handle *h, int32_t n_images, uint32_t *status /*[N]*
 
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t spg_launch_count(const spg_handle *h);
+/* name of the kernel variant the last launch of a stage used (0 nms_peaks, 1 limb_score, 2 limb_match, 3 assemble);
+ * "" before the first launch.  Profiling aid: lets bench.py label its per-kernel numbers with the ncu kernel name. */
+const char *spg_stage_kernel(const spg_handle *h, int32_t stage);
 
 #ifdef __cplusplus
 }
