@@ -23,6 +23,7 @@
 #include "limb_score.cuh"
 #include "limb_score_persist.cuh"
 #include "nms_peaks.cuh"
+#include "nms_peaks_persist.cuh"
 
 using namespace spg;
 
@@ -123,6 +124,18 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.image_base = base;
     a.thr = (float)p->thre1;
     a.ws = h->ws;
+    if (h->persist && a.use_bulk && nms_persist_smem_bytes(H, W, h->ws.capP) <= h->smem_optin && (size_t)H * W / 4 < 65536 &&
+        (size_t)H * W * sizeof(float) < (1u << 20)) {
+        // one resident CTA per SM: loader, 28 scanners, 3 finishers over a ring of 3 plane slots
+        const size_t psm = nms_persist_smem_bytes(H, W, h->ws.capP);
+        const int items = n * h->ws.K;
+        SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        nms_peaks_persist_kernel<<<std::min(items, h->sm_count), kNmsPThreads, psm, st>>>(a, items);
+        h->stage_kernel[0] = "nms_peaks_persist_kernel";
+        h->launches++;
+        SPG_CUDA(h, cudaGetLastError());
+        return SPG_OK;
+    }
     const size_t smem = nms_smem_bytes(a.band_rows, H, W, h->ws.capP);
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "map width %d needs %zu B of shared memory per band", W, smem);
     SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
