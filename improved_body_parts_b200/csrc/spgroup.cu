@@ -44,7 +44,7 @@ struct spg_handle {
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
     const char *stage_kernel[4] = {"", "", "", ""};
-    int persist = 1;  // persistent warp-specialised limb_score when it applies (SPG_SCORE_PERSIST=0 turns it off)
+    int persist = 1;  // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
@@ -288,7 +288,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
-    if (const char *e = getenv("SPG_SCORE_PERSIST")) h->persist = !(e[0] == '0');
+    if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
     DeviceGuard guard(h->device);
 
     const size_t N = cfg->max_batch, K = cfg->n_parts, L = cfg->n_limbs, J = cfg->n_out_joints;

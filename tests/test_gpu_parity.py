@@ -269,25 +269,30 @@ def test_screen_is_conservative_and_effective(env, monkeypatch):
     assert frac < 0.5
 
 
-def test_persistent_and_per_item_scoring_kernels_agree(env, monkeypatch):
-    """limb_score has two schedules (persistent ring for f32 planes that fit it, one CTA per item otherwise): same
-    candidates, hence identical results downstream; both equal to the checker."""
+def test_persistent_and_per_item_kernels_agree(env, monkeypatch):
+    """nms_peaks and limb_score have two schedules (persistent ring for f32 planes that fit it, one CTA per item
+    otherwise): same peaks and candidates, hence identical results downstream; both equal to the checker."""
     t = env.torch
     heat, paf = env.synth.make_batch(60606, 24, 128, 128, 22, drop_prob=0.1, stretch=4, spikes=10, edge=True, colocate=2)
     params = env.skeleton.default_params()
     hd, pd = t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev)
     outs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("SPG_SCORE_PERSIST", flag)
+        monkeypatch.setenv("SPG_PERSIST", flag)
         g = env.Grouper(max_batch=24)
         g.group_device(hd, pd, 128, params)
         outs.append(g.fetch())
+        assert ("persist" in g.stage_kernels()[0]) == (flag == "1") and ("persist" in g.stage_kernels()[1]) == (flag == "1")
         g.close()
     a, b = outs
     assert (a.status == 0).all() and (b.status == 0).all()
-    for f in ("peak_count", "conn_count", "cand_count", "conn_ij", "conn_score", "conn_norm", "n_persons", "subset",
-              "people_xy", "people_score"):
-        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for f in ("peak_count", "peak_x", "peak_y", "peak_score", "peak_anchor", "conn_count", "cand_count", "conn_ij",
+              "conn_score", "conn_norm", "n_persons", "subset", "people_xy", "people_score"):
+        x, y = getattr(a, f), getattr(b, f)
+        if f.startswith("peak_") and f != "peak_count":  # slots beyond the count are undefined
+            m = np.arange(x.shape[2])[None, None, :] < np.minimum(a.peak_count, x.shape[2])[:, :, None]
+            x, y = np.where(m, x, 0), np.where(m, y, 0)
+        assert np.array_equal(x, y), f
     o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, 128, params, threads=4)
     for i in range(24):
         _assert_same(o.as_reference_structures(i), a.as_reference_structures(i), f"image {i}")
