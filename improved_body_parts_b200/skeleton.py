@@ -40,6 +40,11 @@ assert [a for a, _ in LIMBS] == [1, 1, 1, 1, 1, 0, 0, 14, 15, 1, 2, 3, 1, 5, 6, 
 assert [b for _, b in LIMBS] == [0, 14, 15, 16, 17, 14, 15, 16, 17, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13,
                                  2, 5, 8, 12, 11, 9, 2, 5, 11]
 
+#: the 24-limb skeleton of config/config2.py:69-83 (asserted there at :80-83): the limb table is runtime data
+LIMBS_24: Tuple[Tuple[int, int], ...] = tuple(zip(
+    (1, 1, 1, 1, 1, 0, 0, 14, 15, 1, 2, 3, 1, 5, 6, 1, 8, 9, 1, 11, 12, 8, 2, 5),
+    (0, 14, 15, 16, 17, 14, 15, 16, 17, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 11, 16, 17)))
+
 #: network channel layout (config/config.py:96-103): body parts first, then keypoints, then 2 background maps.
 PAF_START, HEAT_START, BKG_START, NUM_LAYERS = 0, NUM_LIMBS, NUM_LIMBS + NUM_PARTS, NUM_LIMBS + NUM_PARTS + 2
 

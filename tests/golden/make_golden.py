@@ -53,18 +53,28 @@ CASES = {
     "single_f64": (dict(seed=26, H=64, W=64, persons=1, **Q), {}, "f64", None),
     "tol_lenrate_p14": (dict(seed=27, H=112, W=112, persons=14, drop_prob=0.35, stretch=6, **Q),
                         dict(len_rate=1.5, connection_tole=1.2), "f32", None),
+    # the 24-limb skeleton of config/config2.py: the limb table is runtime data everywhere
+    "limbs24_p9": (dict(seed=28, H=96, W=104, persons=9, drop_prob=0.1, limbs=skeleton.LIMBS_24, **Q), {}, "f32", None),
 }
 
 
 def main() -> None:
     import torch
 
-    ref = Reference()
+    refs = {}
+    ref = refs.setdefault(skeleton.LIMBS, Reference())
     assert tuple(ref.limbs) == skeleton.LIMBS, "limb table drifted from the reference"
+    only = set(sys.argv[1:])
     manifest = {"generated_by": "tests/golden/make_golden.py", "reference": "hellojialee/Improved-Body-Parts",
                 "numpy": np.__version__, "torch": torch.__version__, "python": sys.version.split()[0], "cases": {}}
+    if only and os.path.exists(os.path.join(HERE, "MANIFEST.json")):
+        manifest["cases"] = json.load(open(os.path.join(HERE, "MANIFEST.json")))["cases"]
     for name, (gen, over, dt, extent) in CASES.items():
+        if only and name not in only:
+            continue
         gen = dict(gen)
+        limbs = tuple(gen.get("limbs", skeleton.LIMBS))
+        ref = refs.setdefault(limbs, Reference(limbs=limbs))
         seed = gen.pop("seed")
         H, W, P = gen.pop("H"), gen.pop("W"), gen.pop("persons")
         heat, paf = synth.make_image(seed, H, W, P, **gen)
@@ -77,7 +87,8 @@ def main() -> None:
                             ext, params)
         dt_s = time.time() - t0
         path = os.path.join(HERE, name + ".npz")
-        save_case(path, heat, paf, skeleton.LIMBS, ext, params, structs,
+        gen.pop("limbs", None)
+        save_case(path, heat, paf, limbs, ext, params, structs,
                   meta=dict(seed=seed, H=H, W=W, persons=P, gen=gen, paf_dtype=dt))
         peaks, conn, special, subset, cand = structs
         manifest["cases"][name] = dict(

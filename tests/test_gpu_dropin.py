@@ -27,6 +27,7 @@ def dropin(cuda_device):
 @pytest.mark.parametrize("path", GOLDENS, ids=[os.path.basename(p)[:-4] for p in GOLDENS])
 def test_three_call_sites_chain_like_process(dropin, path):
     case = load_case(path)
+    dropin.configure(limbs=case["limbs"])  # evaluate.limbSeq (install() takes it from the module)
     heat_hwc = np.ascontiguousarray(case["heat"].transpose(1, 2, 0))
     paf_hwc = np.ascontiguousarray(case["paf"].transpose(1, 2, 0))
     params = case["params"]
@@ -42,6 +43,7 @@ def test_three_call_sites_chain_like_process(dropin, path):
 
 def test_fused_group_and_keypoints(dropin):
     case = load_case([p for p in GOLDENS if "clean_p10_128" in p][0])
+    dropin.configure(limbs=case["limbs"])
     heat_hwc = np.ascontiguousarray(case["heat"].transpose(1, 2, 0))
     paf_hwc = np.ascontiguousarray(case["paf"].transpose(1, 2, 0))
     got = dropin.group(heat_hwc, paf_hwc, case["image_extent"], case["params"])

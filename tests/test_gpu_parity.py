@@ -33,10 +33,10 @@ def env(cuda_device):
     return e
 
 
-def _run_gpu(env, heat, paf, extent, params, **cfg):
+def _run_gpu(env, heat, paf, extent, params, limbs=None, **cfg):
     t = env.torch
     N, K, H, W = heat.shape
-    g = env.Grouper(max_batch=N, max_h=H, max_w=W, **cfg)
+    g = env.Grouper(limbs if limbs is not None else env.skeleton.LIMBS, max_batch=N, max_h=H, max_w=W, **cfg)
     try:
         g.group_device(t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev), extent, params)
         return g.fetch()
@@ -55,7 +55,7 @@ def _assert_same(ref_structs, got_structs, what):
 def test_cuda_matches_reference_golden(env, path):
     case = load_case(path)
     H, W = case["heat"].shape[1:]
-    r = _run_gpu(env, case["heat"][None], case["paf"][None], case["image_extent"], case["params"],
+    r = _run_gpu(env, case["heat"][None], case["paf"][None], case["image_extent"], case["params"], limbs=case["limbs"],
                  max_peaks_per_part=128, max_person_rows=128)
     assert r.status[0] == 0, f"status {r.status[0]:#x}"
     got = r.as_reference_structures(0)
@@ -296,3 +296,21 @@ def test_persistent_and_per_item_kernels_agree(env, monkeypatch):
     o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, 128, params, threads=4)
     for i in range(24):
         _assert_same(o.as_reference_structures(i), a.as_reference_structures(i), f"image {i}")
+
+
+def test_arbitrary_limb_tables(env):
+    """The limb table is runtime data (the reference ships 24-, 30- and 49-limb skeletons): a random 40-limb table over
+    the 18 parts, including repeated and reversed part pairs, against the checker."""
+    rng = np.random.default_rng(5)
+    limbs = []
+    while len(limbs) < 40:
+        a, b = (int(v) for v in rng.choice(18, size=2, replace=False))
+        limbs.append((a, b))
+    heat, paf = env.synth.make_batch(9001, 6, 96, 96, 7, limbs=limbs, drop_prob=0.05)
+    params = env.skeleton.default_params()
+    o = env.so.group_batch(heat, paf, limbs, 96, params)
+    assert (o.status == 0).all()
+    r = _run_gpu(env, heat, paf, 96, params, limbs=limbs)
+    assert (r.status == 0).all()
+    for i in range(6):
+        _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
