@@ -314,3 +314,19 @@ def test_arbitrary_limb_tables(env):
     assert (r.status == 0).all()
     for i in range(6):
         _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
+
+
+def test_random_parameters_and_dirt_against_the_checker(env):
+    """40 seeded draws of (hyper-parameters x dirty-input knobs x map shape): every combination the CUDA path can be
+    configured with must reproduce the checker, floats included.  Covers offset_radius 0..4, mid_num 1..40 (per-m
+    tables), connect_ration / thresholds that move maxfail, remove_recon, len_rate / connection_tole rejects."""
+    from test_oracle_vs_reference import fuzz_cases  # the same draws are checked against the live reference on CPU
+
+    for trial, heat, paf, extent, params, cap in fuzz_cases(40):
+        o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, extent, params)
+        r = _run_gpu(env, heat, paf, extent, params, max_peaks_per_part=cap, max_person_rows=128)
+        what = f"trial {trial}: {heat.shape[2]}x{heat.shape[3]} {params} paf={paf.dtype} extent={extent} capP={cap}"
+        assert (o.status == 0).all(), what
+        assert (r.status == 0).all(), what + f" status {r.status}"
+        for i in range(3):
+            _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), what + f" image {i}")
