@@ -36,6 +36,7 @@ METRIC = "grouping images/sec @128x128 heatmaps, 30 persons/img"
 UNIT = "images/s"
 H = W = 128
 BASE_SEED = 20260921
+CAP_ROWS = 64  # person-row capacity of the handles (<= 40 persons/image in this workload; overflow would trip the status assert)
 
 
 def parse_args():
@@ -56,6 +57,7 @@ def workload_config(args, world):
                         f"{args.persons} persons/img",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "persons": args.persons, "H": H, "W": W,
             "keypoint_channels": 18, "limb_channels": 30,
+            "capacities": {"max_peaks_per_part": 64, "max_cands_per_limb": 1024, "max_person_rows": CAP_ROWS},
             "parallelism": f"image-sharded x{world}" + (" + NCCL gather of person lists to rank 0, overlapped with the next step (two workspaces used alternately)" if world > 1 else ""),
             "l2": f"inputs {args.batch * 48 * H * W * 4 / 1e6:.0f} MB/GPU > 126 MB L2: every step streams from HBM, no flush needed"}
 
@@ -184,7 +186,7 @@ def run_ours(args, rank, world, local_rank):
     # handle k%2's workspace while step k+1 runs on the other handle -- no staging copy, the transfer overlaps compute.
     # The timed region ends only after the last gather has completed.  At N = 1 only handle 0 is used.
     n_handles = 2 if world > 1 else 1
-    groupers = [Grouper(max_batch=B, max_h=H, max_w=W, device=local_rank) for _ in range(n_handles)]
+    groupers = [Grouper(max_batch=B, max_h=H, max_w=W, max_person_rows=CAP_ROWS, device=local_rank) for _ in range(n_handles)]
     g = groupers[0]
     all_views = [x.device_tensors() for x in groupers]
     views = all_views[0]
