@@ -100,7 +100,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // Same, for waits that can be long (role hand-offs in persistent kernels): pass a suspend-time hint so the warp is
 // parked by the hardware instead of polling, and does not take issue slots from the warps it is waiting for.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000u) {
     uint32_t ok = 0;
     while (!ok) {
         asm volatile(
@@ -110,7 +110,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
             " selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
             : "memory");
     }
 }

@@ -16,8 +16,8 @@
 //      1/64-px fixed point from one FFMA) and counts a failure only when it is CERTAIN: the position is
 //      at least 1.5/64 px away from a rounding boundary (so it rounds to the same pixel as the reference's
 //      f64 position) and the map value there is <= thre2.  More than maxfail certain failures => the reference rejects the pair => drop it.
-//      Anything uncertain (near-boundary sample, sample count m near a rounding boundary, end points close
-//      to the border, coincident end points) survives.  The screen can only drop pairs the reference
+//      Anything uncertain (near-boundary sample, sample count m near a rounding boundary, an end point that
+//      is not inside the map [0, W-1] x [0, H-1], coincident end points) survives.  The screen can only drop pairs the reference
 //      drops; it never decides an accept.
 //   B. EXACT, one thread per surviving pair: the reference's arithmetic operation for operation --
 //      f64 np.linspace positions, half-to-even rounding, SEQUENTIAL sum of the samples in the plane's
@@ -36,6 +36,7 @@ struct ScoreArgs {
     const void *paf;
     int64_t img_stride, chan_stride;  // elements
     int H, W, image_base, mid_num, screen, debug;  // debug: bench-only knobs of the persistent kernel (0 in production)
+    int exact_warps;                                 // persistent kernel: scorer warps (the rest screen)
     double image_extent, thre2, connect_ration;
     Workspace ws;
 };
@@ -62,7 +63,8 @@ struct PairGeom {  // one limb's end-point lists in shared memory
 };
 
 // Phase B: the reference's evaluation of one pair (evaluate.py:224-255).  Returns true if it is a candidate.
-template <typename T>
+// kExactBatch: samples of the exact evaluation whose index computations and loads are in flight together (register budget)
+template <typename T, int kExactBatch = 4>
 __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, int H, int W, const ScoreArgs &a,
                                                  const PairGeom &g, int i, int j, bool interior, T thre2,
                                                  double &score, double &prio, bool &bad) {
@@ -96,16 +98,32 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
     T sum = (T)0;
     int above = 0;
     if (interior) {
-        // both end points round to pixels at least 1 px inside the map and samples stay between them:
-        // no index can leave the map, no negative index can wrap
+        // both end points lie inside the map ([0, W-1] x [0, H-1]) and the samples stay between them (to within an
+        // f64 rounding error): no index can leave the map, no negative index can wrap
+        // The m-1 samples before the end point, kExactBatch at a time: all index computations and loads of a batch are
+        // independent and in flight together (the plane may be read through L2); samples past m-1 read a valid address
+        // (sample 0) and are not accumulated, so no sample sees a different operation sequence.
+        const int last = m - 1;
         double td = 0.0;
-        for (int t = 0; t < m - 1; t++) {
-            const int xi = __double2int_rn(__dadd_rn(__dmul_rn(td, stepx), ax));
-            const int yi = __double2int_rn(__dadd_rn(__dmul_rn(td, stepy), ay));            // :235 nearest neighbour
-            const T v = plane[yi * W + xi];
-            sum = sum + v;  // sequential, in sample order, in the plane's precision (:241)
-            above += v > thre2;
-            td = __dadd_rn(td, 1.0);
+        for (int t0 = 0; t0 < last; t0 += kExactBatch) {
+            T vv[kExactBatch];
+#pragma unroll
+            for (int u = 0; u < kExactBatch; u++) {
+                const double tdu = t0 + u < last ? __dadd_rn(td, (double)u) : 0.0;
+                // :235 nearest neighbour, half-to-even: x + 1.5 * 2^52 leaves round(x) in the low word for |x| < 2^31
+                // (a DADD instead of F2I.F64 on the quarter-rate conversion pipe)
+                const int xi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepx), ax), 6755399441055744.0));
+                const int yi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepy), ay), 6755399441055744.0));
+                vv[u] = plane[yi * W + xi];
+            }
+#pragma unroll
+            for (int u = 0; u < kExactBatch; u++) {
+                if (t0 + u < last) {
+                    sum = sum + vv[u];  // sequential, in sample order, in the plane's precision (:241)
+                    above += vv[u] > thre2;
+                }
+            }
+            td = __dadd_rn(td, (double)kExactBatch);
         }
         const T v = m > 1 ? plane[__double2int_rn(by) * W + __double2int_rn(bx)]
                           : plane[__double2int_rn(ay) * W + __double2int_rn(ax)];
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     float *s_fay = s_fax + capP;
     float *s_fbx = s_fay + capP;
     float *s_fby = s_fbx + capP;
-    unsigned char *s_ain = reinterpret_cast<unsigned char *>(s_fby + capP);  // end point safely inside the map
+    unsigned char *s_ain = reinterpret_cast<unsigned char *>(s_fby + capP);  // end point inside the map
     unsigned char *s_bin = s_ain + capP;
     const size_t peaks_bytes = ((size_t)capP * (4 * sizeof(double) + 6 * sizeof(float) + 2) + 15) & ~(size_t)15;
     // per-m tables: reciprocals (phase B), screen sample positions, 64/(m-1), #samples, maxfail
@@ -224,7 +242,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     // end-point lists (refined float coordinates + peak scores), overlapped with the plane copy
     const size_t baseA = ((size_t)n * ws.K + pa) * capP, baseB = ((size_t)n * ws.K + pb) * capP;
     auto inside = [&](double x, double y) {
-        return x >= 1.0 && x <= (double)(W - 2) && y >= 1.0 && y <= (double)(H - 2);
+        return x >= 0.0 && x <= (double)(W - 1) && y >= 0.0 && y <= (double)(H - 1);
     };
     // warp-specialised prologue: warp 0 stages the A list, warp 1 the B list, warps 2-3 build the per-m tables;
     // the other warps go straight to the barrier (the prologue is pure issue overhead for them)

@@ -298,6 +298,28 @@ def test_persistent_and_per_item_kernels_agree(env, monkeypatch):
         _assert_same(o.as_reference_structures(i), a.as_reference_structures(i), f"image {i}")
 
 
+def test_survivor_list_overflow_is_evaluated_in_place(env, monkeypatch):
+    """With the screen off every pair survives; 40 persons give ~1 600 pairs per limb, more than the persistent
+    kernel's survivor list holds, so the screeners evaluate the excess themselves (from the staged plane) while the
+    scorers read the rest back through L2.  Same results as the checker, and every pair accounted for."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(515, 6, 128, 128, 40)
+    params = env.skeleton.default_params()
+    monkeypatch.setenv("SPG_NO_SCREEN", "1")
+    g = env.Grouper(max_batch=6)
+    g.group_device(t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev), 128, params)
+    got = g.fetch()
+    surv = g.device_tensors()["surv_count"][:6].cpu().numpy()
+    assert "persist" in g.stage_kernels()[1]
+    g.close()
+    assert (got.status == 0).all()
+    pairs = np.array([[got.peak_count[i, x] * got.peak_count[i, y] for x, y in env.skeleton.LIMBS] for i in range(6)])
+    assert pairs.max() > 1024 and np.array_equal(surv, pairs)
+    o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, 128, params, threads=4)
+    for i in range(6):
+        _assert_same(o.as_reference_structures(i), got.as_reference_structures(i), f"image {i}")
+
+
 def test_arbitrary_limb_tables(env):
     """The limb table is runtime data (the reference ships 24-, 30- and 49-limb skeletons): a random 40-limb table over
     the 18 parts, including repeated and reversed part pairs, against the checker."""
