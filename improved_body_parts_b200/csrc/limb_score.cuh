@@ -64,7 +64,7 @@ struct PairGeom {  // one limb's end-point lists in shared memory
 
 // Phase B: the reference's evaluation of one pair (evaluate.py:224-255).  Returns true if it is a candidate.
 // kExactBatch: samples of the exact evaluation whose index computations and loads are in flight together (register budget)
-template <typename T, int kExactBatch = 4>
+template <typename T, int kExactBatch = 1>
 __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, int H, int W, const ScoreArgs &a,
                                                  const PairGeom &g, int i, int j, bool interior, T thre2,
                                                  double &score, double &prio, bool &bad) {
@@ -100,30 +100,43 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
     if (interior) {
         // both end points lie inside the map ([0, W-1] x [0, H-1]) and the samples stay between them (to within an
         // f64 rounding error): no index can leave the map, no negative index can wrap
-        // The m-1 samples before the end point, kExactBatch at a time: all index computations and loads of a batch are
-        // independent and in flight together (the plane may be read through L2); samples past m-1 read a valid address
-        // (sample 0) and are not accumulated, so no sample sees a different operation sequence.
         const int last = m - 1;
         double td = 0.0;
-        for (int t0 = 0; t0 < last; t0 += kExactBatch) {
-            T vv[kExactBatch];
-#pragma unroll
-            for (int u = 0; u < kExactBatch; u++) {
-                const double tdu = t0 + u < last ? __dadd_rn(td, (double)u) : 0.0;
+        if constexpr (kExactBatch <= 1) {
+            // plane in shared memory, tight register budget: the plain loop
+#pragma unroll 4
+            for (int t = 0; t < last; t++) {
                 // :235 nearest neighbour, half-to-even: x + 1.5 * 2^52 leaves round(x) in the low word for |x| < 2^31
                 // (a DADD instead of F2I.F64 on the quarter-rate conversion pipe)
-                const int xi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepx), ax), 6755399441055744.0));
-                const int yi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepy), ay), 6755399441055744.0));
-                vv[u] = plane[yi * W + xi];
+                const int xi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(td, stepx), ax), 6755399441055744.0));
+                const int yi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(td, stepy), ay), 6755399441055744.0));
+                const T v = plane[yi * W + xi];
+                sum = sum + v;  // sequential, in sample order, in the plane's precision (:241)
+                above += v > thre2;
+                td = __dadd_rn(td, 1.0);
             }
+        } else {
+            // The m-1 samples before the end point, kExactBatch at a time: all index computations and loads of a batch
+            // are independent and in flight together (the plane is read through L2); samples past m-1 read a valid
+            // address (sample 0) and are not accumulated, so no sample sees a different operation sequence.
+            for (int t0 = 0; t0 < last; t0 += kExactBatch) {
+                T vv[kExactBatch > 0 ? kExactBatch : 1];
 #pragma unroll
-            for (int u = 0; u < kExactBatch; u++) {
-                if (t0 + u < last) {
-                    sum = sum + vv[u];  // sequential, in sample order, in the plane's precision (:241)
-                    above += vv[u] > thre2;
+                for (int u = 0; u < kExactBatch; u++) {
+                    const double tdu = t0 + u < last ? __dadd_rn(td, (double)u) : 0.0;
+                    const int xi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepx), ax), 6755399441055744.0));
+                    const int yi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(tdu, stepy), ay), 6755399441055744.0));
+                    vv[u] = plane[yi * W + xi];
                 }
+#pragma unroll
+                for (int u = 0; u < kExactBatch; u++) {
+                    if (t0 + u < last) {
+                        sum = sum + vv[u];  // sequential, in sample order, in the plane's precision (:241)
+                        above += vv[u] > thre2;
+                    }
+                }
+                td = __dadd_rn(td, (double)kExactBatch);
             }
-            td = __dadd_rn(td, (double)kExactBatch);
         }
         const T v = m > 1 ? plane[__double2int_rn(by) * W + __double2int_rn(bx)]
                           : plane[__double2int_rn(ay) * W + __double2int_rn(ax)];

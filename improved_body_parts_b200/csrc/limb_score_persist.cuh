@@ -36,6 +36,7 @@ constexpr int kPersistSlots = 3;   // plane ring
 constexpr int kMetaSlots = 5;      // end-point lists + survivor list + counters ring
 constexpr int kWorkerWarps = kPersistThreads / 32 - 1;  // 31
 constexpr int kPersistMaxCapP = 64;
+constexpr int kScreenTailBypass = 4;
 constexpr int kPersistListCap = 1024;  // survivors queued per item; the (rare) excess is evaluated inline by the screener
 
 struct PersistHdr {
@@ -58,7 +59,7 @@ struct alignas(16) MetaSlot {
     PeakSlot peaks;
     uint16_t list[kPersistListCap];
     PersistHdr hdr;
-    int nsurv, ncand, bnext;
+    int nsurv, ncand, bnext;  // survivors appended, candidates written, next exact chunk
     uint32_t flags;
 };
 
@@ -74,18 +75,23 @@ __host__ __device__ inline size_t persist_tables_bytes() {
     return (((size_t)(kScreenMaxMid + 1) * (sizeof(double) + kScreenSamples * sizeof(float) + sizeof(ScreenTab))) + 15) &
            ~(size_t)15;
 }
+constexpr size_t kPersistPlaneOffset =
+    ((((size_t)(kScreenMaxMid + 1) * (sizeof(double) + kScreenSamples * sizeof(float) + sizeof(ScreenTab)) + 15) & ~(size_t)15) +
+     kMetaSlots * sizeof(MetaSlot) + 127) & ~(size_t)127;
 inline size_t persist_smem_bytes(size_t plane_bytes, int /*capP*/) {
     const size_t plane = (plane_bytes + 127) & ~(size_t)127;
-    return kPersistSlots * plane + kMetaSlots * sizeof(MetaSlot) + persist_tables_bytes() + 256;
+    return kPersistPlaneOffset + kPersistSlots * plane + 128;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr uint32_t kScreenBias = 0x4B400000u >> 6;
+
 struct ScreenCtx {
     const PeakSlot *ps;
-    const float *plane;
+    uint32_t base;  // shared-memory address of the plane, minus the rounding bias (see screen_pair)
     const ScreenTab *tab;
     const float *ts;  // [kScreenMaxMid + 1][kScreenSamples]
     int W, mid_num, nB;
@@ -104,7 +110,9 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
     const float2 fa = c.ps->fa[i], fb = c.ps->fb[jj];
     const float dx64 = fb.x - fa.x, dy64 = fb.y - fa.y;
     const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
-    const float qf = n2 * rsqrtf(n2) + 1.0f;                          // approximate norm + 1
+    float rs;  // one MUFU.RSQ, no denormal fix-up: n2 below 1e-6 is not screened anyway
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+    const float qf = n2 * rs + 1.0f;  // approximate norm + 1 (NaN for n2 = 0: falls out below)
     const float r = rintf(qf);
     const bool longp = qf >= (float)c.mid_num + 0.51f;
     int m = longp ? c.mid_num : min((int)r, c.mid_num);
@@ -121,17 +129,31 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
     const float ax64o = fa.x + 33.0f, ay64o = fa.y + 33.0f;
     const float *ts = c.ts + m * kScreenSamples;
     const int qmax = __reduce_max_sync(0xffffffffu, qn);
+    // Round-to-nearest-even through the 1.5 * 2^23 trick (positions are in [0, 2^22)): the low bits of the float
+    // pos + 1.5 * 2^23 are the rounded position u (an FADD instead of F2I, which runs on the quarter-rate conversion
+    // pipe).  The bias is never subtracted: its low 6 bits are zero, so bits & 63 == u & 63, and bits >> 6 ==
+    // (u >> 6) + kScreenBias; the kScreenBias * (W + 1) elements that adds to the index are taken off the plane's address once
+    // (kScreenBias; the offset comes from shared memory so that it stays ONE register operand instead of being
+    // re-split into immediates at every sample)
+    const uint32_t base = c.base;
     fails = 0;
-#pragma unroll
-    for (int q2 = 0; q2 < kScreenSamples; q2++) {
-        if (q2 >= qmax) break;
+    auto sample = [&](int q2) {
         const float tf = ts[q2];
-        // round-to-nearest-even through the 1.5 * 2^23 trick (positions are in [0, 2^22)): FADD + IADD instead of
-        // F2I, which runs on the quarter-rate conversion pipe
-        const int xu = __float_as_int(__fadd_rn(__fmaf_rn(tf, sx64, ax64o), 12582912.0f)) - 0x4B400000;
-        const int yu = __float_as_int(__fadd_rn(__fmaf_rn(tf, sy64, ay64o), 12582912.0f)) - 0x4B400000;
-        const float v = c.plane[(yu >> 6) * c.W + (xu >> 6)];
-        fails += (int)(q2 < qn) & (int)(min((unsigned)xu & 63u, (unsigned)yu & 63u) > 2u) & (int)!(v > c.thre2);
+        const uint32_t xb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sx64, ax64o), 12582912.0f));
+        const uint32_t yb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sy64, ay64o), 12582912.0f));
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * ((yb >> 6) * (uint32_t)c.W + (xb >> 6))));
+        fails += (int)(q2 < qn) & (int)(min(xb & 63u, yb & 63u) > 2u) & (int)!(v > c.thre2);
+    };
+    if (qmax == kScreenSamples) {  // the common case (a warp with at least one pair of >= mid_num samples): no trip checks
+#pragma unroll
+        for (int q2 = 0; q2 < kScreenSamples; q2++) sample(q2);
+    } else {
+#pragma unroll
+        for (int q2 = 0; q2 < kScreenSamples; q2++) {
+            if (q2 >= qmax) break;
+            sample(q2);
+        }
     }
 }
 
@@ -140,6 +162,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     // full: plane copy landed + lists published; pfree: every screener has left the plane; screened: the survivor
     // list is complete; mfree: every scorer has left the meta slot
     __shared__ uint64_t bar_full[kPersistSlots], bar_pfree[kPersistSlots], bar_screened[kMetaSlots], bar_mfree[kMetaSlots];
+    __shared__ uint32_t s_bias_bytes;  // 4 * kScreenBias * (W + 1)
 
     using T = float;
     const Workspace &ws = a.ws;
@@ -147,11 +170,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     const int H = a.H, W = a.W, capP = ws.capP, L = ws.L;
     const size_t plane_bytes = (size_t)H * W * sizeof(T);
     const size_t plane_stride = (plane_bytes + 127) & ~(size_t)127;
-    MetaSlot *s_meta = reinterpret_cast<MetaSlot *>(smem_raw + kPersistSlots * plane_stride);
-    unsigned char *tables = reinterpret_cast<unsigned char *>(s_meta + kMetaSlots);
-    double *s_rcp = reinterpret_cast<double *>(tables);
+    // layout: per-m tables, meta ring, then the plane ring -- everything but the planes at compile-time offsets
+    double *s_rcp = reinterpret_cast<double *>(smem_raw);
     ScreenTab *s_tab = reinterpret_cast<ScreenTab *>(s_rcp + (kScreenMaxMid + 1));
     float *s_ts = reinterpret_cast<float *>(s_tab + (kScreenMaxMid + 1));
+    MetaSlot *s_meta = reinterpret_cast<MetaSlot *>(smem_raw + persist_tables_bytes());
+    unsigned char *s_planes = smem_raw + kPersistPlaneOffset;
     const int nE = min(max(a.exact_warps, 1), kWorkerWarps - 1), nS = kWorkerWarps - nE;  // scorer / screener warps
 
     // ---- one-time set-up
@@ -165,6 +189,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             mbar_init(&bar_mfree[e], nE);
             s_meta[e].nsurv = 0; s_meta[e].ncand = 0; s_meta[e].bnext = 0; s_meta[e].flags = 0;
         }
+        s_bias_bytes = 4u * kScreenBias * (uint32_t)(W + 1);
         fence_mbar_init();
     }
     if (tid >= 32 && tid < 32 + kScreenMaxMid + 1) {
@@ -243,7 +268,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             const int n = a.image_base + n_local;
             if (lane == 0) {  // plane first (arrival 1 of 2 on `full`, carries the byte count)
                 const unsigned char *gplane = reinterpret_cast<const unsigned char *>(plane_of(n_local, k));
-                unsigned char *dst = smem_raw + s * plane_stride;
+                unsigned char *dst = s_planes + s * plane_stride;
                 mbar_expect_tx(&bar_full[s], (uint32_t)plane_bytes);
                 for (size_t off = 0; off < plane_bytes; off += kBulkChunkBytes) {
                     const uint32_t bytes = (uint32_t)min((size_t)kBulkChunkBytes, plane_bytes - off);
@@ -330,12 +355,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 MetaSlot &ms = s_meta[e];
                 const int npairs = ms.hdr.npairs;
                 if (c0 * 32 < npairs) {  // warps without pairs skip the item
-                    const T *plane = reinterpret_cast<const T *>(smem_raw + s * plane_stride);
-                    const ScreenCtx sc{&ms.peaks, plane, s_tab, s_ts, W, a.mid_num, ms.hdr.nB, ms.hdr.magic, thre2};
+                    const T *plane = reinterpret_cast<const T *>(s_planes + s * plane_stride);
+                    const ScreenCtx sc{&ms.peaks, smem_u32(plane) - *(volatile uint32_t *)&s_bias_bytes, s_tab, s_ts, W, a.mid_num,
+                                       ms.hdr.nB, ms.hdr.magic, thre2};
                     for (int c = c0; c * 32 < npairs; c += nS) {
                         const int p = c * 32 + lane;
                         bool keep = p < npairs;
-                        if (screen) {
+                        // a last chunk of only a few pairs (31 x 31 peaks leave 1) is not worth a pass: they go straight to
+                        // the exact phase, where they ride along in a chunk that exists anyway
+                        if (screen && npairs - c * 32 > kScreenTailBypass) {
                             int fails, qn, maxfail;
                             screen_pair(sc, min(p, npairs - 1), keep, fails, qn, maxfail);
                             if (qn > 0) keep = fails <= maxfail;

@@ -191,7 +191,7 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     a.screen = h->screen;
     a.debug = 0;
     if (const char *e = getenv("SPG_DEBUG_PERSIST")) a.debug = atoi(e);
-    a.exact_warps = 8;
+    a.exact_warps = 12;
     if (const char *e = getenv("SPG_EXACT_WARPS")) a.exact_warps = std::max(1, std::min(16, atoi(e)));  // tuning knob
     a.ws = h->ws;
     h->cand_dtype = dtype;
