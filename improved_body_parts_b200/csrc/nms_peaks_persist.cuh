@@ -22,6 +22,7 @@ constexpr int kNmsPSlots = 3;
 constexpr int kNmsPFinishers = 3;
 constexpr int kNmsPLists = 2 * kNmsPFinishers;
 constexpr int kNmsPScanners = kNmsPThreads / 32 - 1 - kNmsPFinishers;  // 28
+constexpr int kNmsPMaxIter = 5;  // 32-lane passes over a scanner's slice: 3 planes must fit in shared memory, so a slice is <= 160 float4 groups
 
 inline size_t nms_persist_smem_bytes(int H, int W, int capP) {
     const size_t plane = (((size_t)H * W * sizeof(float)) + 127) & ~(size_t)127;
@@ -96,18 +97,28 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
             if (j >= kNmsPLists) mbar_wait_sleep(&bar_lfree[l], ((j / kNmsPLists) - 1) & 1);
             const float *buf = reinterpret_cast<const float *>(smem_raw + s * plane_stride);
             uint32_t *list = s_lists + (size_t)l * capP;
-            // ---- pass 1: queue the float4 groups of this warp's slice that reach thre1
-            int nq = 0;
-            for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
-                const int g = g0 + lane;
+            // ---- pass 1: queue the float4 groups of this warp's slice that reach thre1.  First only the votes (one
+            // load, three max, one compare, one ballot per 128 elements -- the common case is an empty mask), then the
+            // queue from the masks.
+            uint32_t am[kNmsPMaxIter];
+#pragma unroll
+            for (int it = 0; it < kNmsPMaxIter; it++) {
+                const int g = g_lo + it * 32 + lane;
                 bool act = false;
                 if (g < g_hi) {
                     const float4 c4 = *reinterpret_cast<const float4 *>(buf + 4 * (size_t)g);
                     act = fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)) >= thr;
                 }
-                const uint32_t am = __ballot_sync(0xffffffffu, act);
-                if (act) wq[nq + __popc(am & ((1u << lane) - 1u))] = (uint16_t)g;
-                nq += __popc(am);
+                am[it] = __ballot_sync(0xffffffffu, act);
+            }
+            int nq = 0;
+#pragma unroll
+            for (int it = 0; it < kNmsPMaxIter; it++) {
+                const uint32_t m = am[it];
+                if (m) {  // warp-uniform
+                    if ((m >> lane) & 1u) wq[nq + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g_lo + it * 32 + lane);
+                    nq += __popc(m);
+                }
             }
             __syncwarp();
             // ---- pass 2: 8-neighbour test (neighbours clamped to the image == window clipped to the image)

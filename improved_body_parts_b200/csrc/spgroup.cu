@@ -125,7 +125,8 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.thr = (float)p->thre1;
     a.ws = h->ws;
     if (h->persist && a.use_bulk && nms_persist_smem_bytes(H, W, h->ws.capP) <= h->smem_optin && (size_t)H * W / 4 < 65536 &&
-        (size_t)H * W * sizeof(float) < (1u << 20)) {
+        (size_t)H * W * sizeof(float) < (1u << 20) &&
+        ((size_t)H * W / 4 + kNmsPScanners - 1) / kNmsPScanners <= (size_t)32 * kNmsPMaxIter) {
         // one resident CTA per SM: loader, 28 scanners, 3 finishers over a ring of 3 plane slots
         const size_t psm = nms_persist_smem_bytes(H, W, h->ws.capP);
         const int items = n * h->ws.K;
