@@ -136,6 +136,10 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
     // (kScreenBias; the offset comes from shared memory so that it stays ONE register operand instead of being
     // re-split into immediates at every sample)
     const uint32_t base = c.base;
+    // Every lane runs the warp's maximum number of samples; a lane with fewer samples of its own re-reads padded
+    // entries of its row (its last sample, or sample 0 of the empty row), which can only repeat a failure it has
+    // already counted -- so instead of masking those samples out one by one, the lane's tolerance is raised by their
+    // number: more than maxfail + padded counted failures still means more than maxfail real ones.
     fails = 0;
     auto sample = [&](int q2) {
         const float tf = ts[q2];
@@ -143,7 +147,7 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
         const uint32_t yb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sy64, ay64o), 12582912.0f));
         float v;
         asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * ((yb >> 6) * (uint32_t)c.W + (xb >> 6))));
-        fails += (int)(q2 < qn) & (int)(min(xb & 63u, yb & 63u) > 2u) & (int)!(v > c.thre2);
+        fails += (int)(min(xb & 63u, yb & 63u) > 2u) & (int)!(v > c.thre2);
     };
     if (qmax == kScreenSamples) {  // the common case (a warp with at least one pair of >= mid_num samples): no trip checks
 #pragma unroll
@@ -155,6 +159,7 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
             sample(q2);
         }
     }
+    maxfail += qmax - qn;
 }
 
 __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {

@@ -193,7 +193,7 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     a.debug = 0;
     if (const char *e = getenv("SPG_DEBUG_PERSIST")) a.debug = atoi(e);
     a.exact_warps = 12;
-    if (const char *e = getenv("SPG_EXACT_WARPS")) a.exact_warps = std::max(1, std::min(16, atoi(e)));  // tuning knob
+    if (const char *e = getenv("SPG_EXACT_WARPS")) a.exact_warps = std::max(1, std::min(30, atoi(e)));  // tuning knob (the kernel keeps at least one screener)
     a.ws = h->ws;
     h->cand_dtype = dtype;
     return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);

@@ -320,6 +320,21 @@ def test_survivor_list_overflow_is_evaluated_in_place(env, monkeypatch):
         _assert_same(o.as_reference_structures(i), got.as_reference_structures(i), f"image {i}")
 
 
+@pytest.mark.parametrize("scorers", ["1", "5", "30"])
+def test_role_split_does_not_change_results(env, monkeypatch, scorers):
+    """The persistent limb_score kernel splits its 31 worker warps into screeners and scorers (SPG_EXACT_WARPS, a
+    tuning knob): any split -- one scorer for everything, one screener for everything -- gives the checker's results."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(31337, 12, 128, 128, 26, drop_prob=0.05, spikes=6, colocate=1)
+    params = env.skeleton.default_params()
+    monkeypatch.setenv("SPG_EXACT_WARPS", scorers)
+    got = _run_gpu(env, heat, paf, 128, params)
+    assert (got.status == 0).all()
+    o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, 128, params, threads=4)
+    for i in range(12):
+        _assert_same(o.as_reference_structures(i), got.as_reference_structures(i), f"scorers={scorers} image {i}")
+
+
 def test_arbitrary_limb_tables(env):
     """The limb table is runtime data (the reference ships 24-, 30- and 49-limb skeletons): a random 40-limb table over
     the 18 parts, including repeated and reversed part pairs, against the checker."""
