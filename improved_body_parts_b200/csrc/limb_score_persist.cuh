@@ -7,7 +7,7 @@
 // three roles and two rings:
 //
 //   loader    (warp 0)     issues the plane's bulk copy (TMA, SASS UBLKCP) into one of 3 plane slots as soon as the
-//                          screeners have left it, and publishes the item's two end-point lists -- fetched into
+//                          screeners have left its previous item, and publishes the item's two end-point lists -- fetched into
 //                          registers one item earlier, so no global latency sits on the critical path -- into one of
 //                          kMetaSlots meta slots, and closes items (counters, status) when their meta slot comes
 //                          back.
@@ -164,9 +164,9 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
 
 __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // full: plane copy landed + lists published; pfree: every screener has left the plane; screened: the survivor
-    // list is complete; mfree: every scorer has left the meta slot
-    __shared__ uint64_t bar_full[kPersistSlots], bar_pfree[kPersistSlots], bar_screened[kMetaSlots], bar_mfree[kMetaSlots];
+    // full: plane copy landed + lists published; screened: every screener has left the item -- its survivor list is
+    // complete (scorers) and its plane slot can be refilled (loader); mfree: every scorer has left the meta slot
+    __shared__ uint64_t bar_full[kPersistSlots], bar_screened[kMetaSlots], bar_mfree[kMetaSlots];
     __shared__ uint32_t s_bias_bytes;  // 4 * kScreenBias * (W + 1)
 
     using T = float;
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     if (tid == 0) {
         for (int s = 0; s < kPersistSlots; s++) {
             mbar_init(&bar_full[s], 2);  // plane copy (expect_tx) + end-point lists
-            mbar_init(&bar_pfree[s], nS);
         }
         for (int e = 0; e < kMetaSlots; e++) {
             mbar_init(&bar_screened[e], nS);
@@ -267,7 +266,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
         if (nj > 0) fetch(0);
         for (int j = 0; j < nj; j++) {
             const int s = j % kPersistSlots, e = j % kMetaSlots;
-            if (j >= kPersistSlots) mbar_wait_sleep(&bar_pfree[s], ((j / kPersistSlots) - 1) & 1);
+            if (j >= kPersistSlots) {  // the plane slot's previous item has been screened
+                const int jp = j - kPersistSlots;
+                mbar_wait_sleep(&bar_screened[jp % kMetaSlots], (jp / kMetaSlots) & 1);
+            }
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / L, k = item - n_local * L;
             const int n = a.image_base + n_local;
@@ -387,10 +389,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                     }
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bar_pfree[s]);     // this warp no longer reads the plane slot
-                    mbar_arrive(&bar_screened[e]);  // release: this warp's survivors are in the list
-                }
+                if (lane == 0) mbar_arrive(&bar_screened[e]);  // release: this warp's survivors are in the list, the plane is no longer read
                 if (++c0 == nS) c0 = 0;
             }
         } else {
@@ -403,6 +402,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 if (ns > 0) {
                     const T *gplane = plane_of(ms.hdr.n - a.image_base, ms.hdr.k);  // the plane's slot may already hold another item
                     for (;;) {
+                        if (*(volatile int *)&ms.bnext * 32 >= ns) break;  // all chunks taken: no need to draw a number
                         int c = 0;
                         if (lane == 0) c = atomicAdd(&ms.bnext, 1);
                         c = __shfl_sync(0xffffffffu, c, 0);
