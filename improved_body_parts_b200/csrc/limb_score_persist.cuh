@@ -7,10 +7,10 @@
 // three roles and two rings:
 //
 //   loader    (warp 0)     issues the plane's bulk copy (TMA, SASS UBLKCP) into one of 3 plane slots as soon as the
-//                          screeners have left its previous item, and publishes the item's two end-point lists -- fetched into
-//                          registers one item earlier, so no global latency sits on the critical path -- into one of
-//                          kMetaSlots meta slots, and closes items (counters, status) when their meta slot comes
-//                          back.
+//                          screeners have left the slot's previous item, and publishes the item's two end-point
+//                          lists -- fetched into registers one item earlier, so no global latency sits on the
+//                          critical path -- into one of kMetaSlots meta slots; it closes items (counters, status)
+//                          when their meta slot comes back.
 //   screeners (most warps) the f32 screen of every pair of the item, one chunk of 32 pairs per warp and pass;
 //                          survivors are appended, warp-aggregated, to the meta slot's list.  When a screener
 //                          leaves an item it releases the PLANE slot: the exact phase does not hold it.
