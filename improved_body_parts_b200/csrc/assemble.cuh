@@ -37,6 +37,7 @@ struct AssembleArgs {
     int n_images, image_base, use_bulk;
     double len_rate, connection_tole, min_mean_score;
     int remove_recon, min_parts;
+    int refresh_len_check;  // demo_image.py:414-415: the same-B refresh also checks the limb length
     Workspace ws;
 };
 
@@ -164,6 +165,7 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
             t.owner[B * capP + jb] = (short)j;
         }
     } else if (scB <= s) {  // same B, refresh its score (:368-380)
+        if (a.refresh_len_check && reach <= len) return 0;  // demo_image.py:414-415 only
         const double sub = __dadd_rn((double)t.ps[B * capP + jb], scB);
         t.total[j] = __dadd_rn(__dsub_rn(t.total[j], sub), add);
         t.sc[B * capR + j] = s;
@@ -302,6 +304,11 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     double *g_score = ws.people_score + (size_t)n * capR;
     const double *g_px = ws.peak_x + (size_t)n * K * capP;
     const double *g_py = ws.peak_y + (size_t)n * K * capP;
+    // wire record (include/spgroup.h): rows are staged in shared memory -- the connection tables are dead by now -- and
+    // leave in one coalesced copy, so a record in a peer GPU's memory costs a few 128-byte NVLink writes per image
+    const int WR = 2 * J + 1;
+    const bool wire_on = ws.wire != nullptr && (size_t)min(ws.wire_rows, capR) * WR * sizeof(double) <= assemble_conn_bytes(L, capP);
+    double *s_wire = reinterpret_cast<double *>(smem_raw);
     // keep flags first (reusing `touch`), then each kept row's output position = number of kept rows born earlier
     for (int j = lane; j < nrows; j += 32) {
         bool keep = false;
@@ -331,7 +338,10 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         row[K * 2 + 1] = -1.0;
         row[(K + 1) * 2 + 0] = (double)t.cnt[j];
         row[(K + 1) * 2 + 1] = t.maxlen[j];
-        g_score[o] = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
+        const double pscore = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
+        g_score[o] = pscore;
+        const bool wrow = wire_on && o < ws.wire_rows;
+        if (wrow) s_wire[(size_t)o * WR + 2 * J] = pscore;
         for (int g = 0; g < J; g++) {                         // :523-539
             const int part = ws.out_from_part[g];
             const int id = ((mj >> part) & 1u) ? t.id[part * capR + j] : -1;
@@ -343,11 +353,29 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
             }
             g_xy[((size_t)o * J + g) * 2 + 0] = x;
             g_xy[((size_t)o * J + g) * 2 + 1] = y;
+            if (wrow) {
+                s_wire[(size_t)o * WR + 2 * g + 0] = x;
+                s_wire[(size_t)o * WR + 2 * g + 1] = y;
+            }
         }
     }
+    if (ws.wire != nullptr && (!wire_on || out > ws.wire_rows)) flags |= kStWireOverflow;
+    uint32_t st_word = 0;
     if (lane == 0) {
         ws.n_persons[n] = out;
-        if (flags) atomicOr(&ws.status[n], flags);
+        st_word = flags ? (atomicOr(&ws.status[n], flags) | flags) : ws.status[n];
+    }
+    if (ws.wire != nullptr) {
+        __syncwarp();
+        const size_t rec_bytes = 8 + (size_t)ws.wire_rows * WR * sizeof(double);
+        unsigned char *rec = ws.wire + (size_t)(ws.wire_first + (long long)blockIdx.x) * rec_bytes;
+        const int wn = wire_on ? min(out, ws.wire_rows) : 0;
+        if (lane == 0) {
+            reinterpret_cast<int *>(rec)[0] = wn;
+            reinterpret_cast<uint32_t *>(rec)[1] = st_word;
+        }
+        double *rows = reinterpret_cast<double *>(rec + 8);
+        for (int i = lane; i < wn * WR; i += 32) rows[i] = s_wire[i];
     }
 }
 

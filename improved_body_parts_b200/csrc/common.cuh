@@ -27,10 +27,12 @@ constexpr uint32_t kStCandOverflow = 1u << 1;
 constexpr uint32_t kStRowOverflow = 1u << 2;
 constexpr uint32_t kStSampleIndex = 1u << 3;
 constexpr uint32_t kStAssert = 1u << 4;
+constexpr uint32_t kStWireOverflow = 1u << 5;
 
 struct Params {
     double thre1, thre2, connect_ration, len_rate, connection_tole, min_mean_score;
     int32_t mid_num, offset_radius, remove_recon, min_parts;
+    int32_t crit1_strict, refresh_len_check;  // demo_image.py's two deviations from evaluate.py (0 = evaluate.py)
 };
 
 // Device workspace of one handle (all arrays [max_batch][...]).
@@ -59,6 +61,10 @@ struct Workspace {
     double *people_xy;             // [N][capR][J][2]
     double *people_score;          // [N][capR]
     uint32_t *status;              // [N]
+    // wire records (include/spgroup.h "wire records"); wire == nullptr: off.  May point into a peer GPU's memory.
+    unsigned char *wire;
+    long long wire_first;          // record index of image 0 of a call
+    int wire_rows;                 // person rows per record
 };
 
 // ---------------------------------------------------------------------------------------------

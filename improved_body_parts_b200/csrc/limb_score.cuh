@@ -35,7 +35,9 @@ namespace spg {
 struct ScoreArgs {
     const void *paf;
     int64_t img_stride, chan_stride;  // elements
-    int H, W, image_base, mid_num, screen, debug;  // debug: bench-only knobs of the persistent kernel (0 in production)
+    int H, W, image_base, mid_num, screen;
+    int debug;                                       // only read in -DSPG_DEBUG builds (timing experiments); always 0 otherwise
+    int crit1_strict;                                // demo_image.py:288 compares with `>` where evaluate.py:246 uses `>=`
     int exact_warps;                                 // persistent kernel: scorer warps (the rest screen)
     double image_extent, thre2, connect_ration;
     Workspace ws;
@@ -90,10 +92,16 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
     // RN(q0 + r*y) is the correctly rounded quotient (tests/test_numerics.py checks it against exact rationals).
     double stepx = 0.0, stepy = 0.0;
     if (m > 1) {
-        const double dd = (double)(m - 1), y = g.rcp[m - 1];
-        const double qx = __dmul_rn(vx, y), qy = __dmul_rn(vy, y);
-        stepx = __fma_rn(__fma_rn(-qx, dd, vx), y, qx);
-        stepy = __fma_rn(__fma_rn(-qy, dd, vy), y, qy);
+        const double dd = (double)(m - 1);
+        if (m - 1 <= kScreenMaxMid) {
+            const double y = g.rcp[m - 1];
+            const double qx = __dmul_rn(vx, y), qy = __dmul_rn(vy, y);
+            stepx = __fma_rn(__fma_rn(-qx, dd, vx), y, qx);
+            stepy = __fma_rn(__fma_rn(-qy, dd, vy), y, qy);
+        } else {  // mid_num beyond the reciprocal table (the reference accepts any mid_num): the plain correctly rounded division
+            stepx = __ddiv_rn(vx, dd);
+            stepy = __ddiv_rn(vy, dd);
+        }
     }
     T sum = (T)0;
     int above = 0;
@@ -178,7 +186,8 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
         prio = __dadd_rn(__dadd_rn(__dmul_rn(0.5, score), (double)__fmul_rn(0.25f, g.as[i])),
                          (double)__fmul_rn(0.25f, g.bs[j]));
     }
-    const bool crit1 = (double)above >= __dmul_rn(a.connect_ration, (double)m);             // :246
+    const double need = __dmul_rn(a.connect_ration, (double)m);
+    const bool crit1 = a.crit1_strict ? (double)above > need : (double)above >= need;       // :246 (demo_image.py:288: `>`)
     const bool crit2 = score > 0.0;                                                         // :251
     return crit1 && crit2;
 }
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
             // fewest samples that must exceed thre2: smallest integer >= connect_ration*m in f64, as :246 compares
             const double need = __dmul_rn(a.connect_ration, (double)m);
             int need_i = (int)need;
-            if ((double)need_i < need) need_i++;
+            if ((double)need_i < need || (a.crit1_strict && (double)need_i == need)) need_i++;  // strict: smallest integer > need
             s_maxfail[m] = (signed char)max(min(m - need_i, 127), -1);
             s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
             s_inv64[m] = m > 1 ? 1.0f / (float)(m - 1) : 0.0f;

@@ -31,6 +31,12 @@
 
 namespace spg {
 
+#ifdef SPG_DEBUG
+#define SPG_DBG(x) (x)
+#else
+#define SPG_DBG(x) false
+#endif
+
 constexpr int kPersistThreads = 1024;
 constexpr int kPersistSlots = 3;   // plane ring
 constexpr int kMetaSlots = 5;      // end-point lists + survivor list + counters ring
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
         const int m = tid - 32;
         const double need = __dmul_rn(a.connect_ration, (double)m);  // :246 compares in f64
         int need_i = (int)need;
-        if ((double)need_i < need) need_i++;
+        if ((double)need_i < need || (a.crit1_strict && (double)need_i == need)) need_i++;  // strict: smallest integer > need
         s_rcp[m] = m > 0 ? __ddiv_rn(1.0, (double)m) : 0.0;
         // up to kScreenSamples samples spread over the interior [lo, hi] (the ends sit on the peaks and rarely fail)
         const int lo = m / 8, hi = m - 1 - lo;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             const bool special = nA == 0 || nB == 0;
             if (lane == 0) {
                 PersistHdr h;
-                h.nA = nA; h.nB = nB; h.npairs = (special || a.debug == 1) ? 0 : nA * nB; h.n = n; h.k = k; h.special = special;
+                h.nA = nA; h.nB = nB; h.npairs = (special || SPG_DBG(a.debug == 1)) ? 0 : nA * nB; h.n = n; h.k = k; h.special = special;
                 h.magic = nB > 1 ? 0xffffffffu / (uint32_t)nB + 1u : 0u;
                 h.pad = 0;
                 ms.hdr = h;
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 const int e = j % kMetaSlots;
                 mbar_wait_sleep(&bar_screened[e], (j / kMetaSlots) & 1);  // every screener has left item j: the list is complete
                 MetaSlot &ms = s_meta[e];
-                const int ns = a.debug == 2 ? 0 : min(ms.nsurv, kPersistListCap);
+                const int ns = SPG_DBG(a.debug == 2) ? 0 : min(ms.nsurv, kPersistListCap);
                 if (ns > 0) {
                     const T *gplane = plane_of(ms.hdr.n - a.image_base, ms.hdr.k);  // the plane's slot may already hold another item
                     for (;;) {

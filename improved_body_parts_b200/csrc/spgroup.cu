@@ -44,8 +44,10 @@ struct spg_handle {
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
     const char *stage_kernel[4] = {"", "", "", ""};
-    int persist = 1;  // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
-    int screen = 1;  // limb_score phase A on (SPG_NO_SCREEN=1 in the environment turns it off, for A/B tests)
+    // tuning / A-B switches, read from the environment ONCE in spg_create (never per launch); none changes a result
+    int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
+    int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
+    int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
     std::string err;
@@ -190,10 +192,12 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     a.thre2 = p->thre2;
     a.connect_ration = p->connect_ration;
     a.screen = h->screen;
+    a.crit1_strict = p->crit1_strict != 0;
     a.debug = 0;
+#ifdef SPG_DEBUG  // timing-only knobs that change results exist only in -DSPG_DEBUG builds (never in the shipped library)
     if (const char *e = getenv("SPG_DEBUG_PERSIST")) a.debug = atoi(e);
-    a.exact_warps = 12;
-    if (const char *e = getenv("SPG_EXACT_WARPS")) a.exact_warps = std::max(1, std::min(30, atoi(e)));  // tuning knob (the kernel keeps at least one screener)
+#endif
+    a.exact_warps = h->exact_warps;
     a.ws = h->ws;
     h->cand_dtype = dtype;
     return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);
@@ -225,7 +229,9 @@ int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStr
     a.min_mean_score = p->min_mean_score;
     a.remove_recon = p->remove_recon;
     a.min_parts = p->min_parts;
+    a.refresh_len_check = p->refresh_len_check != 0;
     a.ws = h->ws;
+    a.ws.wire_first += base;  // records are indexed by the image's position in the call
     a.use_bulk = ((size_t)h->ws.L * h->ws.capP * sizeof(uint32_t)) % 16 == 0;  // bulk copies move multiples of 16 bytes
     const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR) + assemble_conn_bytes(h->ws.L, h->ws.capP);
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "capacities need %zu B of shared memory in assemble (limit %zu)", smem, h->smem_optin);
@@ -246,6 +252,19 @@ int run_all(spg_handle *h, const float *heat, int64_t his, int64_t hcs, const vo
     if ((rc = launch_match(h, base, n, st))) return rc;
     if ((rc = launch_assemble(h, base, n, p, st))) return rc;
     return SPG_OK;
+}
+
+__global__ void wire_signal_kernel(unsigned long long *word, unsigned long long value) {
+    __threadfence_system();  // everything earlier on the stream has completed; order it before the flag for every observer
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(word), "l"(value) : "memory");
+}
+
+__global__ void wire_wait_kernel(const unsigned long long *word, unsigned long long value) {
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+        if (v < value) __nanosleep(500);
+    } while (v < value);
 }
 
 }  // namespace
@@ -292,6 +311,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
+    if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener
     DeviceGuard guard(h->device);
 
     const size_t N = cfg->max_batch, K = cfg->n_parts, L = cfg->n_limbs, J = cfg->n_out_joints;
@@ -360,6 +380,102 @@ int spg_get_device_view(const spg_handle *h, spg_device_view *v) {
     v->subset = ws.subset; v->n_persons = ws.n_persons; v->people_xy = ws.people_xy; v->people_score = ws.people_score;
     v->status = ws.status;
     return SPG_OK;
+}
+
+// ---- wire records + peer memory + stream-ordered signalling ------------------------------------------------------
+int64_t spg_wire_record_bytes(const spg_handle *h) {
+    if (!h) return 0;
+    const int rows = h->ws.wire_rows > 0 ? h->ws.wire_rows : h->ws.capR;
+    return 8 + (int64_t)rows * (2 * h->ws.J + 1) * (int64_t)sizeof(double);
+}
+
+int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int32_t wire_rows) {
+    if (!h) return SPG_E_INVALID;
+    if (!wire_dev) {
+        h->ws.wire = nullptr;
+        h->ws.wire_first = 0;
+        return SPG_OK;
+    }
+    if (wire_rows < 1 || wire_rows > h->ws.capR) return fail(h, SPG_E_INVALID, "wire_rows %d outside [1, max_person_rows=%d]", wire_rows, h->ws.capR);
+    if (first_record < 0) return fail(h, SPG_E_INVALID, "first_record is negative");
+    if ((reinterpret_cast<uintptr_t>(wire_dev) & 7) != 0) return fail(h, SPG_E_INVALID, "wire buffer must be 8-byte aligned");
+    if ((size_t)wire_rows * (2 * h->ws.J + 1) * sizeof(double) > assemble_conn_bytes(h->ws.L, h->ws.capP))
+        return fail(h, SPG_E_INVALID, "wire_rows %d do not fit the assemble kernel's staging area", wire_rows);
+    h->ws.wire = static_cast<unsigned char *>(wire_dev);
+    h->ws.wire_first = first_record;
+    h->ws.wire_rows = wire_rows;
+    return SPG_OK;
+}
+
+int spg_wire_create(int32_t device, uint64_t bytes, void **dev_ptr, unsigned char ipc_handle[64]) {
+    if (!dev_ptr || !ipc_handle || bytes == 0) return SPG_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(device);
+    void *p = nullptr;
+    // a dedicated cudaMalloc allocation: an IPC handle exports the whole allocation it points into
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(nullptr, SPG_E_CUDA, "cudaMalloc of %llu wire bytes failed", (unsigned long long)bytes);
+    cudaIpcMemHandle_t hd;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&hd, p) != cudaSuccess) {
+        const char *why = cudaGetErrorString(cudaGetLastError());
+        cudaFree(p);
+        return fail(nullptr, SPG_E_CUDA, "exporting the wire buffer failed: %s", why);
+    }
+    memcpy(ipc_handle, &hd, 64);
+    *dev_ptr = p;
+    return SPG_OK;
+}
+
+int spg_wire_open(int32_t device, const unsigned char ipc_handle[64], void **peer_ptr) {
+    if (!peer_ptr || !ipc_handle) return SPG_E_INVALID;
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, 64);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, SPG_E_CUDA, "cudaIpcOpenMemHandle failed: %s (no peer access between the two GPUs?)", cudaGetErrorString(e));
+    }
+    *peer_ptr = p;
+    return SPG_OK;
+}
+
+int spg_wire_close(void *peer_ptr) { return (!peer_ptr || cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess) ? SPG_OK : SPG_E_CUDA; }
+
+int spg_wire_destroy(int32_t device, void *dev_ptr) {
+    if (!dev_ptr) return SPG_OK;
+    DeviceGuard guard(device);
+    cudaDeviceSynchronize();
+    return cudaFree(dev_ptr) == cudaSuccess ? SPG_OK : SPG_E_CUDA;
+}
+
+int spg_wire_signal(int32_t device, uint64_t *word_dev, uint64_t value, void *stream) {
+    if (!word_dev) return SPG_E_INVALID;
+    DeviceGuard guard(device);
+    wire_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(word_dev), value);
+    return cudaGetLastError() == cudaSuccess ? SPG_OK : fail(nullptr, SPG_E_CUDA, "wire_signal launch failed");
+}
+
+int spg_wire_wait(int32_t device, const uint64_t *word_dev, uint64_t value, void *stream) {
+    if (!word_dev) return SPG_E_INVALID;
+    DeviceGuard guard(device);
+    // cuStreamWaitValue64 through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
+    typedef int (*wait_fn_t)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+    static wait_fn_t wait_fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            wait_fn = reinterpret_cast<wait_fn_t>(fn);
+        cudaGetLastError();
+        looked = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (wait_fn && wait_fn(st, (unsigned long long)reinterpret_cast<uintptr_t>(word_dev), value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) == 0) return SPG_OK;
+    // no stream memory operations on this driver: a one-thread polling kernel (sleeps between polls)
+    wire_wait_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const unsigned long long *>(word_dev), value);
+    return cudaGetLastError() == cudaSuccess ? SPG_OK : fail(nullptr, SPG_E_CUDA, "wire_wait launch failed");
 }
 
 int64_t spg_launch_count(const spg_handle *h) { return h ? h->launches : 0; }

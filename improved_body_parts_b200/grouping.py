@@ -18,9 +18,9 @@ from .skeleton import COCO_FROM_PART, LIMBS, NUM_PARTS, GroupParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspgroup.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-ST_PEAK_OVERFLOW, ST_CAND_OVERFLOW, ST_ROW_OVERFLOW, ST_SAMPLE_INDEX, ST_ASSERT = 1, 2, 4, 8, 16
+ST_PEAK_OVERFLOW, ST_CAND_OVERFLOW, ST_ROW_OVERFLOW, ST_SAMPLE_INDEX, ST_ASSERT, ST_WIRE_OVERFLOW = 1, 2, 4, 8, 16, 32
 F32, F64 = 0, 1
 
 #: every symbol include/spgroup.h declares (checked by tests/test_abi.py against the built library)
@@ -28,7 +28,9 @@ EXPORTS = (
     "spg_create", "spg_destroy", "spg_last_error", "spg_abi_version", "spg_get_device_view", "spg_group_batch",
     "spg_group_host", "spg_host_alloc", "spg_host_free", "spg_nms_peaks", "spg_limb_score", "spg_limb_match",
     "spg_assemble", "spg_upload_peaks", "spg_upload_connections", "spg_download_peaks", "spg_download_connections",
-    "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel")
+    "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel", "spg_wire_record_bytes",
+    "spg_set_wire_output", "spg_wire_create", "spg_wire_open", "spg_wire_close", "spg_wire_destroy", "spg_wire_signal",
+    "spg_wire_wait")
 
 
 class GroupingError(RuntimeError):
@@ -46,7 +48,7 @@ class _Params(C.Structure):
     _fields_ = [("thre1", C.c_double), ("thre2", C.c_double), ("connect_ration", C.c_double),
                 ("len_rate", C.c_double), ("connection_tole", C.c_double), ("min_mean_score", C.c_double),
                 ("mid_num", C.c_int32), ("offset_radius", C.c_int32), ("remove_recon", C.c_int32),
-                ("min_parts", C.c_int32)]
+                ("min_parts", C.c_int32), ("crit1_strict", C.c_int32), ("refresh_len_check", C.c_int32)]
 
 
 class _DeviceView(C.Structure):
@@ -77,6 +79,15 @@ def load_library() -> C.CDLL:
         lib.spg_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
         lib.spg_destroy.argtypes = [C.c_void_p]
         lib.spg_destroy.restype = None
+        lib.spg_wire_record_bytes.restype = C.c_int64
+        lib.spg_wire_record_bytes.argtypes = [C.c_void_p]
+        lib.spg_set_wire_output.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        lib.spg_wire_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+        lib.spg_wire_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.spg_wire_close.argtypes = [C.c_void_p]
+        lib.spg_wire_destroy.argtypes = [C.c_int32, C.c_void_p]
+        lib.spg_wire_signal.argtypes = [C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.spg_wire_wait.argtypes = [C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
         if lib.spg_abi_version() != ABI_VERSION:
             raise GroupingError("libspgroup.so ABI version mismatch")
         _lib = lib
@@ -92,7 +103,7 @@ def params_struct(params) -> _Params:
     else:
         gp = GroupParams.from_dict(dict(params))
     return _Params(gp.thre1, gp.thre2, gp.connect_ration, gp.len_rate, gp.connection_tole, gp.min_mean_score,
-                   gp.mid_num, gp.offset_radius, gp.remove_recon, gp.min_parts)
+                   gp.mid_num, gp.offset_radius, gp.remove_recon, gp.min_parts, gp.crit1_strict, gp.refresh_len_check)
 
 
 def _vp(a: Optional[np.ndarray]):

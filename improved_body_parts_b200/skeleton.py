@@ -79,6 +79,10 @@ class GroupParams:
     remove_recon: int = 0
     min_parts: int = 2
     min_mean_score: float = 0.45
+    #: demo_image.py's inlined copy of the grouping code: ``>`` at :288 where evaluate.py:246 has ``>=``,
+    #: and a limb-length check in the same-B refresh (:414-415).  0 = evaluate.py.
+    crit1_strict: int = 0
+    refresh_len_check: int = 0
 
     @classmethod
     def from_dict(cls, params: dict) -> "GroupParams":
@@ -90,8 +94,16 @@ class GroupParams:
 
     def to_dict(self) -> dict:
         d = dataclasses.asdict(self)
-        d.pop("min_parts"), d.pop("min_mean_score")
+        for k in ("min_parts", "min_mean_score", "crit1_strict", "refresh_len_check"):
+            d.pop(k)
         return d
+
+    @classmethod
+    def demo(cls, params: Optional[dict] = None) -> "GroupParams":
+        """The behaviour of demo_image.py's inlined grouping (``:288``, ``:414-415``, ``:533``) for a params dict."""
+        gp = cls.from_dict(dict(params or {}))
+        gp.crit1_strict, gp.refresh_len_check, gp.min_parts = 1, 1, 4
+        return gp
 
 
 def default_params() -> dict:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPG_ABI_VERSION 1
+#define SPG_ABI_VERSION 2
 
 enum {
     SPG_OK = 0,
@@ -46,7 +46,8 @@ enum {
     SPG_ST_ROW_OVERFLOW = 1u << 2,   /* person assembly needed more than max_person_rows rows    */
     SPG_ST_SAMPLE_INDEX = 1u << 3,   /* a line sample fell outside the map: the reference would  */
                                      /* raise IndexError at evaluate.py:235                      */
-    SPG_ST_ASSERT = 1u << 4          /* the reference would raise at evaluate.py:437-439         */
+    SPG_ST_ASSERT = 1u << 4,         /* the reference would raise at evaluate.py:437-439         */
+    SPG_ST_WIRE_OVERFLOW = 1u << 5   /* more persons than the wire record holds (rows beyond are dropped) */
 };
 
 enum { SPG_F32 = 0, SPG_F64 = 1 }; /* dtype of the body-part planes (evaluate.py:86 makes them f64) */
@@ -74,6 +75,10 @@ typedef struct spg_config {
 typedef struct spg_params {
     double thre1, thre2, connect_ration, len_rate, connection_tole, min_mean_score;
     int32_t mid_num, offset_radius, remove_recon, min_parts;
+    /* demo_image.py's inlined copy of the grouping code differs from evaluate.py in two decisions; both 0
+     * for evaluate.py.  With min_parts = 4 (demo_image.py:533) they give the demo's behaviour. */
+    int32_t crit1_strict;       /* 1: `count >  connect_ration*n` (demo_image.py:288) instead of `>=` (evaluate.py:246) */
+    int32_t refresh_len_check;  /* 1: the same-B refresh also requires len_rate*maxlen > len (demo_image.py:414-415)   */
 } spg_params;
 
 /* Device-resident results of the last call, for consumers that stay on the GPU (NCCL gather, benchmarks).
@@ -159,6 +164,40 @@ int spg_download_people(spg_handle *h, int32_t n_images, int32_t *n_persons /*[N
                         double *subset /*[N][cap_rows][K+2][2]*/, double *people_xy /*[N][cap_rows][J][2]*/,
                         double *people_score /*[N][cap_rows]*/, void *stream);
 int spg_download_status(spg_handle *h, int32_t n_images, uint32_t *status /*[N]*/, void *stream);
+
+/* ---- wire records: what leaves the GPU (format_results, evaluate.py:563-582) ------------------------------- */
+/* One fixed-stride record per image: an 8-byte header followed by `rows` person rows of (2*n_out_joints + 1)
+ * doubles -- x0,y0,...,x16,y16 in COCO order (evaluate.py:523-539), then the person score 1 - 1/total (:541) --
+ * i.e. exactly the payload format_results turns into {"keypoints": [x,y,v]*17, "score": s} (v = x>0 or y>0).
+ * Only the first n_persons rows are written; the rest of the slot is never touched, so when the record lives in
+ * another GPU's memory only live rows cross NVLink. */
+typedef struct spg_wire_header {
+    int32_t n_persons;
+    uint32_t status; /* SPG_ST_* bits of the image */
+} spg_wire_header;
+/* bytes of one image's record for this handle: 8 + wire_rows * (2*n_out_joints + 1) * 8 */
+int64_t spg_wire_record_bytes(const spg_handle *h);
+/* Direct the assemble stage to ALSO emit wire records: image i of a call goes to
+ * (char*)wire_dev + (first_record + i) * spg_wire_record_bytes().  `wire_dev` may be local device memory or PEER
+ * memory (another GPU's buffer opened with spg_wire_open: the records then travel over NVLink as the kernel stores
+ * them -- the gather of the person lists fused into the kernel that produces them, no collective kernel).
+ * wire_rows <= max_person_rows caps the rows per record (SPG_ST_WIRE_OVERFLOW).  NULL switches wire output off. */
+int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int32_t wire_rows);
+
+/* ---- peer memory + stream-ordered signalling for the NVLink gather (no NCCL in the data path) ------------ */
+/* A sink is plain device memory that other processes (one per GPU) can map: create it on the owner, send the
+ * 64-byte handle to the peers by any means (torch.distributed), open it there.  Zero-filled on creation. */
+int spg_wire_create(int32_t device, uint64_t bytes, void **dev_ptr, unsigned char ipc_handle[64]);
+int spg_wire_open(int32_t device, const unsigned char ipc_handle[64], void **peer_ptr);
+int spg_wire_close(void *peer_ptr);
+int spg_wire_destroy(int32_t device, void *dev_ptr);
+/* release-store `value` into a 64-bit word (local or peer memory) once everything earlier on `stream` has
+ * completed: a one-thread kernel (fence.sys + st.release.sys).  The producer's "my records have landed". */
+int spg_wire_signal(int32_t device, uint64_t *word_dev, uint64_t value, void *stream);
+/* make `stream` wait until *word_dev >= value.  `word_dev` must be LOCAL device memory: the wait is a stream
+ * memory operation (cuStreamWaitValue64), executed by the copy/compute front end -- no kernel sits on an SM
+ * spinning, so it cannot collide with the persistent kernels that own every SM.  */
+int spg_wire_wait(int32_t device, const uint64_t *word_dev, uint64_t value, void *stream);
 
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t spg_launch_count(const spg_handle *h);

@@ -111,6 +111,50 @@ class Reference:
         return peaks, conns, special, subset, candidate
 
 
+class DemoReference:
+    """The grouping code INLINED in ``demo_image.py``'s ``process()`` (``/root/reference/demo_image.py:185-536``), lifted
+    statement for statement: everything from ``all_peaks = []`` (:185) to the final prune
+    ``subset = np.delete(subset, deleteIdx, axis=0)`` (:536), minus the matplotlib call ``show_color_vector(...)`` (:191).
+    It differs from evaluate.py in three decisions (``>`` at :288, the length check at :414-415,
+    ``count < 4`` at :533); this class is what pins ``GroupParams.demo()`` to it."""
+
+    def __init__(self, limbs=None):
+        import numpy as np
+        import torch
+
+        base = Reference(limbs)
+        path = os.path.join(REFERENCE_ROOT, "demo_image.py")
+        tree = ast.parse(open(path, encoding="utf-8").read())
+        proc = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "process")
+        def is_assign_to(n, name):
+            return isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name) and n.targets[0].id == name
+        start = next(i for i, n in enumerate(proc.body) if is_assign_to(n, "all_peaks"))
+        ends = [i for i, n in enumerate(proc.body) if is_assign_to(n, "subset") and "np.delete" in ast.unparse(n)]
+        assert ends and ends[-1] > start, "demo_image.py layout changed"
+        body = [n for n in proc.body[start:ends[-1] + 1]
+                if not (isinstance(n, ast.Expr) and isinstance(n.value, ast.Call) and "show_color_vector" in ast.unparse(n.value.func))]
+        ret = ast.parse("return all_peaks, connection_all, special_k, subset, candidate").body[0]
+        fn = ast.FunctionDef(name="demo_group", args=ast.arguments(
+            posonlyargs=[], args=[ast.arg(arg=a) for a in ("heatmap_avg", "paf_avg", "oriImg", "params")], kwonlyargs=[],
+            kw_defaults=[], defaults=[]), body=body + [ret], decorator_list=[], type_params=[])
+        mod = ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[]))
+        ns = {"np": np, "math": math, "torch": torch, "util": base.util, "limbSeq": base.limbs}
+        exec(compile(mod, path, "exec"), ns)
+        self._fn, self.limbs = ns["demo_group"], base.limbs
+
+    def group(self, heat_hwc, paf_hwc, image_extent, params):
+        import warnings
+
+        import numpy as np
+
+        class _Img:  # only oriImg.shape[0] is read (demo_image.py:282)
+            shape = (int(image_extent), 0, 3)
+
+        with _cuda_identity_if_needed(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return self._fn(np.asarray(heat_hwc), np.asarray(paf_hwc), _Img, params)
+
+
 if __name__ == "__main__":
     print("reference available:", reference_available())
     if reference_available():

@@ -51,6 +51,7 @@
 typedef struct spgo_params {
     double thre1, thre2, connect_ration, len_rate, connection_tole, min_mean_score;
     int32_t mid_num, offset_radius, remove_recon, min_parts;
+    int32_t crit1_strict, refresh_len_check; /* demo_image.py:288 (`>`), :414-415 (length check in the same-B refresh); 0 = evaluate.py */
 } spgo_params;
 
 /* Branch counters (tests only): which rarely-taken reference branches an input set reached. */
@@ -279,7 +280,8 @@ int spgo_find_connections(const double *px, const double *py, const float *pscor
                     const float pr = (0.5f * s + 0.25f * pscore[off[a] + i]) + 0.25f * pscore[off[b] + j];
                     prio = (double)pr;
                 }
-                const int crit1 = (double)above >= p->connect_ration * (double)n; /* :246 */
+                const int crit1 = p->crit1_strict ? (double)above > p->connect_ration * (double)n   /* demo_image.py:288 */
+                                                  : (double)above >= p->connect_ration * (double)n; /* :246 */
                 const int crit2 = score > 0.0;                                      /* :251 */
                 if (crit1 && crit2) {
                     cands[nc].i = i; cands[nc].j = j; cands[nc].score = score; cands[nc].norm = norm;
@@ -372,6 +374,7 @@ int spgo_find_people(const float *pscore, const int32_t *part_count, int K, int 
                         SUB(j, K + 1, 1) = len > SUB(j, K + 1, 1) ? len : SUB(j, K + 1, 1);
                     }
                 } else if (SUB(j, B, 1) <= s) {                          /* same B, refresh (:368-380) */
+                    if (p->refresh_len_check && p->len_rate * SUB(j, K + 1, 1) <= len) continue; /* demo_image.py:414-415 */
                     cov(COV_REFRESH);
                     SUB(j, K, 0) -= (double)pscore[idB] + SUB(j, B, 1);
                     SUB(j, B, 0) = (double)idB;

@@ -28,7 +28,7 @@ class _Params(C.Structure):
     _fields_ = [("thre1", C.c_double), ("thre2", C.c_double), ("connect_ration", C.c_double),
                 ("len_rate", C.c_double), ("connection_tole", C.c_double), ("min_mean_score", C.c_double),
                 ("mid_num", C.c_int32), ("offset_radius", C.c_int32), ("remove_recon", C.c_int32),
-                ("min_parts", C.c_int32)]
+                ("min_parts", C.c_int32), ("crit1_strict", C.c_int32), ("refresh_len_check", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -61,7 +61,8 @@ def _params_struct(params: dict) -> _Params:
                    float(params.get("connect_ration", 0.8)), float(params.get("len_rate", 16.0)),
                    float(params.get("connection_tole", 0.7)), float(params.get("min_mean_score", 0.45)),
                    int(params.get("mid_num", 20)), int(params.get("offset_radius", 2)),
-                   int(params.get("remove_recon", 0)), int(params.get("min_parts", 2)))
+                   int(params.get("remove_recon", 0)), int(params.get("min_parts", 2)),
+                   int(params.get("crit1_strict", 0)), int(params.get("refresh_len_check", 0)))
 
 
 def _p(a: np.ndarray):

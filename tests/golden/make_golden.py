@@ -22,10 +22,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
 
 from golden_io import save_case  # noqa: E402
 from improved_body_parts_b200 import skeleton, synth  # noqa: E402
-from oracle.ref_loader import Reference  # noqa: E402
+from oracle.ref_loader import DemoReference, Reference  # noqa: E402
 
 # name -> (make_image kwargs, param overrides, paf dtype, image_extent override or None)
 Q = dict(noise_levels=16)  # quantised noise keeps the fixtures compressible
@@ -55,6 +56,16 @@ CASES = {
                         dict(len_rate=1.5, connection_tole=1.2), "f32", None),
     # the 24-limb skeleton of config/config2.py: the limb table is runtime data everywhere
     "limbs24_p9": (dict(seed=28, H=96, W=104, persons=9, drop_prob=0.1, limbs=skeleton.LIMBS_24, **Q), {}, "f32", None),
+    # demo_image.py's INLINED grouping copy (oracle/ref_loader.DemoReference): `>` at :288, length check at :414-415,
+    # `count < 4` at :533.  The stored params carry crit1_strict / refresh_len_check / min_parts so that the checker and
+    # the CUDA path are driven into the demo's behaviour; each case is also run through evaluate.py's functions and the
+    # manifest records that the two really differ on it.
+    "demo_default_p20": (dict(seed=32, H=96, W=112, persons=20, drop_prob=0.2, colocate=3, edge=True, **Q), {}, "f64", None,
+                         "demo"),
+    "demo_crit1_tie_p14": (dict(seed=43, H=96, W=112, persons=14, drop_prob=0.3, stretch=6, spikes=10, **Q),
+                           dict(mid_num=10, thre2=0.3), "f32", None, "demo"),
+    "demo_refresh_len_p14": (dict(seed=50, H=96, W=112, persons=14, drop_prob=0.3, stretch=6, spikes=10, **Q),
+                             dict(len_rate=1.5, connection_tole=1.2), "f32", None, "demo"),
 }
 
 
@@ -62,19 +73,21 @@ def main() -> None:
     import torch
 
     refs = {}
-    ref = refs.setdefault(skeleton.LIMBS, Reference())
+    ref = refs.setdefault((skeleton.LIMBS, "evaluate"), Reference())
     assert tuple(ref.limbs) == skeleton.LIMBS, "limb table drifted from the reference"
     only = set(sys.argv[1:])
     manifest = {"generated_by": "tests/golden/make_golden.py", "reference": "hellojialee/Improved-Body-Parts",
                 "numpy": np.__version__, "torch": torch.__version__, "python": sys.version.split()[0], "cases": {}}
     if only and os.path.exists(os.path.join(HERE, "MANIFEST.json")):
         manifest["cases"] = json.load(open(os.path.join(HERE, "MANIFEST.json")))["cases"]
-    for name, (gen, over, dt, extent) in CASES.items():
+    for name, case in CASES.items():
+        gen, over, dt, extent = case[:4]
+        variant = case[4] if len(case) > 4 else "evaluate"
         if only and name not in only:
             continue
         gen = dict(gen)
         limbs = tuple(gen.get("limbs", skeleton.LIMBS))
-        ref = refs.setdefault(limbs, Reference(limbs=limbs))
+        ref = refs.setdefault((limbs, variant), (DemoReference if variant == "demo" else Reference)(limbs=limbs))
         seed = gen.pop("seed")
         H, W, P = gen.pop("H"), gen.pop("W"), gen.pop("persons")
         heat, paf = synth.make_image(seed, H, W, P, **gen)
@@ -86,16 +99,23 @@ def main() -> None:
         structs = ref.group(np.ascontiguousarray(heat.transpose(1, 2, 0)), np.ascontiguousarray(paf.transpose(1, 2, 0)),
                             ext, params)
         dt_s = time.time() - t0
+        differs = None
+        if variant == "demo":
+            from parity import diff_structures
+            ev = refs.setdefault((limbs, "evaluate"), Reference(limbs=limbs)).group(
+                np.ascontiguousarray(heat.transpose(1, 2, 0)), np.ascontiguousarray(paf.transpose(1, 2, 0)), ext, params)
+            differs = bool(diff_structures(ev, structs, 0.0))
+            params = dict(params, crit1_strict=1, refresh_len_check=1, min_parts=4)  # drives checker + CUDA into the demo's behaviour
         path = os.path.join(HERE, name + ".npz")
         gen.pop("limbs", None)
         save_case(path, heat, paf, limbs, ext, params, structs,
-                  meta=dict(seed=seed, H=H, W=W, persons=P, gen=gen, paf_dtype=dt))
+                  meta=dict(seed=seed, H=H, W=W, persons=P, gen=gen, paf_dtype=dt, variant=variant))
         peaks, conn, special, subset, cand = structs
         manifest["cases"][name] = dict(
             peaks=int(sum(len(p) for p in peaks)),
             connections=int(sum(0 if isinstance(c, list) else c.shape[0] for c in conn)),
             special_k=len(special), persons=int(subset.shape[0]), reference_seconds=round(dt_s, 3),
-            bytes=os.path.getsize(path))
+            bytes=os.path.getsize(path), **({"source": "demo_image.py:185-536", "differs_from_evaluate_py": differs} if variant == "demo" else {}))
         print(f"{name:28s} {manifest['cases'][name]}")
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1)
