@@ -4,68 +4,134 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] ...                 # the reference's CPU algorithm (Python port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, images sharded (weak scaling)
+    python bench.py --config {p30,p10,f64,512}                      # the other single-GPU configurations (default p30)
 
-A "step" is one pass of the hot path (peaks -> candidate scoring -> greedy matching -> person assembly, the
-window /root/reference/evaluate.py:507-513 times) over one batch of 256 images per GPU; at N > 1 it ends with an
-NCCL gather of the person lists to rank 0.  One JSON line is printed by rank 0:
+One pass = the hot path (peaks -> candidate scoring -> greedy matching -> person assembly + wire records, the window
+/root/reference/evaluate.py:507-513 times plus the format_results payload) over one batch of images resident in HBM.
+A "step" is `passes_per_step` passes (so that K steps time >= 100 ms of device work; every pass streams the whole
+input batch, which is larger than L2, from HBM).  At N > 1 every rank's assemble kernel stores its wire records
+straight into rank 0's sink buffer over NVLink (sharding.PeerWireSink): the gather is part of every pass.
+One JSON line is printed by rank 0:
 
   value      whole-job images/s with the maps already resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the C-ABI host entry point (spg_group_host): pinned HOST maps in, person lists
              back on the host, H2D/D2H inside the timed region
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json's HBM peak
-  kernels    per-kernel event times of the same timed steps
+  kernels    per-kernel event times taken inside the timed steps
   cpu_baseline  the Python/numpy port of the reference's algorithm, one process, same batch (N=1 only)
 """
 from __future__ import annotations
 
 import argparse
+import fcntl
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "grouping images/sec @128x128 heatmaps, 30 persons/img"
 UNIT = "images/s"
-H = W = 128
 BASE_SEED = 20260921
-CAP_ROWS = 64  # person-row capacity of the handles (<= 40 persons/image in this workload; overflow would trip the status assert)
+CAP_ROWS = 64  # person-row capacity of the handles and of a wire record (<= 40 persons/image here; overflow trips the status assert)
+
+# name -> workload.  p30 is the configuration the metric is quoted on (BASELINE configs[2]'s per-GPU shard).
+CONFIGS = {
+    "p30": dict(H=128, W=128, persons=30, batch=256, paf="f32", gen={},
+                what="BASELINE configs[2] per-GPU shard: batch=256/GPU synthetic 128x128x(18+30) f32 maps, 30 persons/img"),
+    "p10": dict(H=128, W=128, persons=10, batch=256, paf="f32", gen={},
+                what="BASELINE configs[1]: batch=256 synthetic 128x128x(18+30) f32 maps, 10 persons/img, 1 GPU"),
+    "f64": dict(H=128, W=128, persons=30, batch=256, paf="f64", gen={},
+                what="configs[2]'s shard with float64 body-part maps -- the dtype predict() emits (evaluate.py:86,161)"),
+    "512": dict(H=512, W=512, persons=30, batch=32, paf="f32", gen=dict(scale_range=(3.2, 5.2), sigma_scale=4.0),
+                what="BASELINE configs[3]'s map size: batch=32 synthetic 512x512x(18+30) f32 maps (bodies and blobs 4x), 30 persons/img"),
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--persons", type=int, default=30)
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="p30")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per pass (0 = the configuration's)")
+    ap.add_argument("--persons", type=int, default=0, help="0 = the configuration's")
+    ap.add_argument("--passes", type=int, default=0, help="passes per step (0 = as many as make K steps >= 100 ms)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: packed NCCL gather instead of NVLink peer stores")
+    ap.add_argument("--unmodified", action="store_true",
+                    help="--impl reference only, build container only: time the UNMODIFIED reference functions (oracle/ref_loader)")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.batch = args.batch or cfg["batch"]
+    args.persons = args.persons or cfg["persons"]
+    args.H, args.W, args.paf = cfg["H"], cfg["W"], cfg["paf"]
+    return args
 
 
-def workload_config(args, world):
-    return {"workload": f"BASELINE configs[2] per-GPU shard: batch={args.batch}/GPU synthetic 128x128x(18+30) f32 maps, "
-                        f"{args.persons} persons/img",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "persons": args.persons, "H": H, "W": W,
-            "keypoint_channels": 18, "limb_channels": 30,
-            "capacities": {"max_peaks_per_part": 64, "max_cands_per_limb": 1024, "max_person_rows": CAP_ROWS},
-            "parallelism": f"image-sharded x{world}" + (" + NCCL gather of person lists to rank 0, overlapped with the next step (two workspaces used alternately)" if world > 1 else ""),
-            "l2": f"inputs {args.batch * 48 * H * W * 4 / 1e6:.0f} MB/GPU > 126 MB L2: every step streams from HBM, no flush needed"}
+def metric_name(args):
+    return f"grouping images/sec @{args.H}x{args.W} heatmaps, {args.persons} persons/img"
+
+
+def workload_config(args, world, passes=None, gather=None):
+    esz = 8 if args.paf == "f64" else 4
+    mb = args.batch * (18 * 4 + 30 * esz) * args.H * args.W / 1e6
+    c = {"workload": CONFIGS[args.config]["what"] if (args.batch, args.persons) == (CONFIGS[args.config]["batch"], CONFIGS[args.config]["persons"])
+         else f"config {args.config} with batch={args.batch}/GPU, {args.persons} persons/img",
+         "name": args.config, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "persons": args.persons,
+         "H": args.H, "W": args.W, "keypoint_channels": 18, "limb_channels": 30, "paf_dtype": args.paf,
+         "capacities": {"max_peaks_per_part": 64, "max_cands_per_limb": 1024, "max_person_rows": CAP_ROWS, "wire_rows": CAP_ROWS},
+         "parallelism": f"image-sharded x{world}" + (f"; person lists reach rank 0 by {gather}" if world > 1 else ""),
+         "l2": f"inputs {mb:.0f} MB/GPU > 126 MB L2: every pass streams from HBM, no flush needed"}
+    if passes is not None:
+        c["passes_per_step"] = passes
+        c["images_per_step"] = args.batch * world * passes
+    return c
 
 
 def make_shard(args, rank):
     from improved_body_parts_b200 import synth
 
-    return synth.make_batch(BASE_SEED + rank * args.batch, args.batch, H, W, args.persons)
+    heat, paf = synth.make_batch(BASE_SEED + rank * args.batch, args.batch, args.H, args.W, args.persons, **CONFIGS[args.config]["gen"])
+    if args.paf == "f64":  # as tests/golden/make_golden.py: values that are not f32-representable
+        paf = paf.astype(np.float64) * (1.0 + 2.0 ** -30) + 2.0 ** -40
+    return heat, paf
+
+
+def build_once():
+    """Every rank calls this; a file lock makes one of them compile while the others wait for the finished library."""
+    import __graft_entry__ as ge
+
+    with open(os.path.join(ROOT, ".build.lock"), "w") as fh:
+        fcntl.flock(fh, fcntl.LOCK_EX)
+        try:
+            ge.build()
+        finally:
+            fcntl.flock(fh, fcntl.LOCK_UN)
+
+
+def host_cpu_budget():
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count() ignores both)."""
+    affinity = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = max(1, int(float(q) / float(period)))
+    except (OSError, ValueError):
+        pass
+    usable = min(affinity, quota) if quota else affinity
+    return {"os_cpu_count": os.cpu_count(), "affinity": affinity, "cgroup_quota_cpus": quota, "usable": usable}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -82,7 +148,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -106,7 +172,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        inside = [r for t, r in self.rows if any(a - 0.06 <= t <= b + 0.06 for a, b in self.windows)]
+        inside = [r for t, r in self.rows if any(a - 0.03 <= t <= b + 0.03 for a, b in self.windows)]
         used, scope = (inside, "timed regions") if len(inside) >= 2 else ([r for _, r in self.rows], "whole run (timed regions shorter than the sampling period)")
         sm, smax, reasons = [], [], set()
         for r in used:
@@ -126,36 +192,71 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (Python/numpy port, oracle/grouping_port.py -- the reference
-    itself is pure Python and cannot travel to this box) on all host cores, one image per task."""
+    """--impl reference: the reference's CPU algorithm on the host cores this process may use, one image per task.
+
+    The reference itself is pure Python and cannot travel to the GPU box, so the arm runs oracle/grouping_port.py --
+    the Python/numpy port that is bit-pinned to reference-generated goldens.  Nothing of the product (no libspgroup.so,
+    no CUDA) is loaded or built here.  With --unmodified (build container only) the UNMODIFIED reference functions are
+    timed instead, single process as the README describes them."""
     if rank != 0:
         return
     from improved_body_parts_b200 import skeleton
     from oracle import grouping_port as gp
 
-    cores = os.cpu_count() or 1
+    cpus = host_cpu_budget()
     heat, paf = make_shard(args, 0)
-    sample = min(args.batch, max(16, cores * 4))
     params = skeleton.default_params()
-    pool, run = gp.make_pool(heat, paf, H, params, skeleton.LIMBS, workers=cores)
-    try:
-        for _ in range(max(args.warmup, 1)):
-            run(range(sample))
+    extra = {}
+    if args.unmodified:
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            raise SystemExit("--unmodified needs /root/reference (build container)")
+        ref = ref_loader.Reference()
+        n = min(args.batch, 4)
+        hw = [np.ascontiguousarray(heat[i].transpose(1, 2, 0)) for i in range(n)]
+        pw = [np.ascontiguousarray(paf[i].transpose(1, 2, 0)) for i in range(n)]
+        ref.group(hw[0], pw[0], args.H, params)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            run(range(sample))
+            for i in range(n):
+                ref.group(hw[i], pw[i], args.H, params)
         dt = time.perf_counter() - t0
-    finally:
-        pool.close()
-        pool.join()
-    value = sample * args.steps / dt
-    cfg = workload_config(args, world)
-    desc = f"{sample} images of the batch per step, fork pool of {cores} processes, one image per task"
+        value, sample, cores, kind = n * args.steps / dt, n, 1, "reference"
+        desc = f"{n} images per step through the UNMODIFIED evaluate.py functions (oracle/ref_loader.py), one process"
+    else:
+        workers = cpus["usable"]
+        sample = min(args.batch, max(16, workers * 4))
+        # single-process figure first (what the README describes), on a few images
+        n1 = min(args.batch, 8)
+        gp.group_image(heat[0], paf[0], args.H, params, skeleton.LIMBS)
+        t0 = time.perf_counter()
+        for i in range(n1):
+            gp.group_image(heat[i], paf[i], args.H, params, skeleton.LIMBS)
+        extra["single_process"] = {"value": n1 / (time.perf_counter() - t0), "unit": UNIT, "images": n1}
+        pool, run = gp.make_pool(heat, paf, args.H, params, skeleton.LIMBS, workers=workers)
+        try:
+            for _ in range(max(args.warmup, 1)):
+                run(range(sample))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                run(range(sample))
+            dt = time.perf_counter() - t0
+        finally:
+            pool.close()
+            pool.join()
+        value, cores, kind = sample * args.steps / dt, workers, "port"
+        desc = (f"{sample} images of the batch per step, fork pool of {workers} processes (= usable CPUs: affinity "
+                f"{cpus['affinity']}, cgroup quota {cpus['cgroup_quota_cpus']}, os.cpu_count {cpus['os_cpu_count']}), one image per task")
+    try:
+        import torch
+        extra["torch_threads"] = torch.get_num_threads()
+    except Exception:
+        pass
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 maps; f64 coordinates", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "vs_baseline": None, "dtype": f"{args.paf} maps; f64 coordinates", "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "cpus": cpus, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -165,8 +266,9 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from improved_body_parts_b200 import skeleton
-    from improved_body_parts_b200.grouping import Grouper
+    from improved_body_parts_b200 import skeleton, wire
+    from improved_body_parts_b200.grouping import Grouper, GroupingError
+    from improved_body_parts_b200.sharding import PackedGather, PeerWireSink
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the grouping path has no CPU fallback")
@@ -175,68 +277,67 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    H, W, B = args.H, args.W, args.batch
     heat_np, paf_np = make_shard(args, rank)
-    B = args.batch
     params = skeleton.default_params()
     heat_pin = torch.from_numpy(heat_np).pin_memory()
     paf_pin = torch.from_numpy(paf_np).pin_memory()
     heat_d = heat_pin.to(dev, non_blocking=True)
     paf_d = paf_pin.to(dev, non_blocking=True)
-    # Two handles used alternately: at N > 1 the person lists of step k are gathered (NCCL, side stream) straight out of
-    # handle k%2's workspace while step k+1 runs on the other handle -- no staging copy, the transfer overlaps compute.
-    # The timed region ends only after the last gather has completed.  At N = 1 only handle 0 is used.
-    n_handles = 2 if world > 1 else 1
-    groupers = [Grouper(max_batch=B, max_h=H, max_w=W, max_person_rows=CAP_ROWS, device=local_rank) for _ in range(n_handles)]
-    g = groupers[0]
-    all_views = [x.device_tensors() for x in groupers]
-    views = all_views[0]
-    from improved_body_parts_b200.sharding import gather_people
-    locals_ = [{"n_persons": v["n_persons"][:B], "people_xy": v["people_xy"][:B], "people_score": v["people_score"][:B]}
-               for v in all_views]
-    gathered = [None]
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    ev_ready = [torch.cuda.Event() for _ in range(n_handles)]
-    ev_done = [torch.cuda.Event() for _ in range(n_handles)]
-    if world > 1:
-        for e in ev_done:
-            e.record(torch.cuda.current_stream())
-    step_no = [0]
-
-    def gather(hi):  # NCCL gather of handle hi's person lists to rank 0 (rank order == image order), on the side stream
-        if world == 1:
-            return
-        main = torch.cuda.current_stream()
-        ev_ready[hi].record(main)
-        comm_stream.wait_event(ev_ready[hi])
-        with torch.cuda.stream(comm_stream):
-            gathered[0] = gather_people(locals_[hi], dst=0)
-            ev_done[hi].record(comm_stream)
-
-    def gather_join():  # make the main stream wait for the outstanding gathers
-        if world > 1:
-            for e in ev_done:
-                torch.cuda.current_stream().wait_event(e)
-
-    n_ev = 6
+    g = Grouper(max_batch=B, max_h=H, max_w=W, max_person_rows=CAP_ROWS, device=local_rank)
+    views = g.device_tensors()
+    rb = g.wire_record_bytes(CAP_ROWS)
     stream = torch.cuda.current_stream()
 
-    def step(evs=None):
-        hi = step_no[0] % n_handles
-        step_no[0] += 1
-        gh = groupers[hi]
-        if world > 1:
-            stream.wait_event(ev_done[hi])  # this handle's previous person lists have left the GPU
+    # ---- where the wire records go: a local buffer at N = 1; rank 0's sink over NVLink at N > 1
+    sink = pg = None
+    local_wire = torch.zeros((B, rb), dtype=torch.uint8, device=dev)
+    gather_how = None
+    if world > 1:
+        if not args.no_peer:
+            try:
+                sink = PeerWireSink(B, rb, local_rank, dst=0)
+                gather_how = "NVLink peer stores from the assemble kernel into rank 0's sink (CUDA IPC; no collective kernel)"
+            except GroupingError as e:
+                gather_how = f"packed NCCL gather (peer mapping unavailable: {e})"
+        if sink is None:
+            pg = PackedGather(B, rb, dev, dst=0)
+            gather_how = gather_how or "one packed NCCL gather per pass (pre-allocated buffers)"
+    cstream = torch.cuda.Stream(device=dev) if (sink is not None and rank == 0) else None
+    pass_no = [0]
+
+    def one_pass(evs=None):
+        s = pass_no[0]
+        pass_no[0] += 1
+        if sink is not None:
+            g.set_wire_output(sink.begin(s, stream), 0, CAP_ROWS)
+        elif pg is not None:
+            g.set_wire_output(pg.local.data_ptr(), 0, CAP_ROWS)
+        else:
+            g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
         if evs: evs[0].record(stream)
-        gh.nms_peaks(heat_d, params)
+        g.nms_peaks(heat_d, params)
         if evs: evs[1].record(stream)
-        gh.limb_score(paf_d, H, params)
+        g.limb_score(paf_d, H, params)
         if evs: evs[2].record(stream)
-        gh.limb_match(B, params)
+        g.limb_match(B, params)
         if evs: evs[3].record(stream)
-        gh.assemble(B, params)
+        g.assemble(B, params)
         if evs: evs[4].record(stream)
-        gather(hi)
+        if sink is not None:
+            sink.publish(s, stream)
+            if rank == 0:  # the consumer: waits for every rank's counters (stream memory ops), then frees the generation
+                sink.collect(s, cstream)
+                sink.release(s, cstream)
+        elif pg is not None:
+            pg.gather()
         if evs: evs[5].record(stream)
+
+    def join_consumer():
+        if cstream is not None:
+            e = torch.cuda.Event()
+            e.record(cstream)
+            stream.wait_event(e)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,59 +349,123 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.start()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    n_ev = 6
+    for _ in range(3):
+        one_pass()
+    join_consumer()
     barrier()
-    # Per-kernel durations come from CUDA events recorded around every kernel of every `stage_every`-th step of the timed
-    # region (an event between two kernels costs ~2.5 us of launch gap, 5 % of a step if every step carries six);
-    # the region itself is bracketed by its own two events.
-    stage_every = max(1, min(5, args.steps // 3))
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(0, args.steps, stage_every)]
+    # ---- passes per step: enough that K steps cover >= 100 ms of device time (same number on every rank)
+    passes = args.passes
+    if passes <= 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(4):
+            one_pass()
+        join_consumer()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 4], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        passes = max(1, min(64, math.ceil(100.0 / (args.steps * float(t.item())))))
+    for _ in range(max(args.warmup, 3)):
+        for _ in range(passes):
+            one_pass()
+    join_consumer()
+    barrier()
+    # Per-kernel durations: CUDA events around every kernel of the FIRST pass of every step of the timed region (an event
+    # between two kernels costs ~2.5 us of launch gap, so not every pass carries them); the region has its own two events.
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
     ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = sum(x.launch_count for x in groupers)
+    l0 = g.launch_count
     w0 = time.time()
     ev_start.record(stream)
     for k in range(args.steps):
-        step(evs[k // stage_every] if k % stage_every == 0 else None)
-    gather_join()
+        for p in range(passes):
+            one_pass(evs[k] if (p == 0 and passes > 1) or (passes == 1 and k % 5 == 0) else None)
+    join_consumer()
     ev_end.record(stream)
     torch.cuda.synchronize()
     w1 = time.time()
-    launches = sum(x.launch_count for x in groupers) - l0
+    launches = g.launch_count - l0
     barrier()
     elapsed_ms = ev_start.elapsed_time(ev_end)
-    stage_ms = [statistics.fmean(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(n_ev - 1)]
+    used = [e for k, e in enumerate(evs) if passes > 1 or k % 5 == 0]
+    stage_ms = [statistics.fmean(e[i].elapsed_time(e[i + 1]) for e in used) for i in range(n_ev - 1)]
     if sampler:
         sampler.window(w0, w1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms / 1e3)
+    n_pass = args.steps * passes
+    value = world * B * n_pass / (elapsed_ms / 1e3)
 
-    # ---- correctness guard inside the bench: statuses clean, persons found
+    # ---- correctness guards inside the bench: statuses clean, persons found, wire records = the device tables,
+    # and at N > 1 what landed on rank 0 is byte for byte what every rank produced
     r_status = views["status"][:B].cpu().numpy()
     r_np = views["n_persons"][:B].cpu().numpy()
     assert (r_status == 0).all(), f"status flags set: {np.unique(r_status)}"
     assert r_np.min() > 0, "no persons found -- the timed path did no work"
-    if world > 1 and rank == 0:
-        got = gathered[0]["n_persons"]
-        assert got.shape[0] == world * B and bool((got[:B].cpu() == views["n_persons"][:B].cpu()).all()), "gathered lists are not in image order"
+    g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
+    g.assemble(B, params)
+    torch.cuda.synchronize()
+    mine = local_wire.cpu().numpy()
+    rec = wire.as_records(mine, 17, CAP_ROWS)
+    assert np.array_equal(rec["n_persons"], r_np) and not rec["status"].any()
+    xy, sc = views["people_xy"][:B].cpu().numpy(), views["people_score"][:B].cpu().numpy()
+    for i in range(0, B, max(1, B // 16)):
+        n = int(r_np[i])
+        assert np.array_equal(rec[i]["rows"]["xy"][:n], xy[i, :n]) and np.array_equal(rec[i]["rows"]["score"][:n], sc[i, :n])
+    gather_ok = None
+    if world > 1:
+        crc = zlib.crc32(mine.tobytes())
+        crcs = [None] * world
+        dist.all_gather_object(crcs, crc)
+        if rank == 0:
+            last = pass_no[0] - 1
+            if sink is not None:
+                landed = sink.collect(last, stream).cpu().numpy()  # already complete: only maps the generation of the last pass
+            else:
+                landed = pg.records().cpu().numpy()
+            got = [zlib.crc32(landed[r * B:(r + 1) * B].tobytes()) for r in range(world)]
+            gather_ok = got == crcs
+            assert gather_ok, f"records on rank 0 differ from what the ranks produced: {got} vs {crcs}"
 
     # ---- e2e: HOST maps -> spg_group_host (H2D + kernels + D2H inside) -> person lists on the host
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     out = None
-    for _ in range(2):
+
+    def host_call(out):
+        # at N > 1 the records of the call also travel to rank 0 (same sink, same hand-shakes as the device-resident passes)
+        s = pass_no[0]
+        pass_no[0] += 1
+        if sink is not None:
+            g.set_wire_output(sink.begin(s, stream), 0, CAP_ROWS)
+            stream.synchronize()  # spg_group_host runs on the library's own streams: the slot must be free before it starts
+        elif pg is not None:
+            g.set_wire_output(pg.local.data_ptr(), 0, CAP_ROWS)
+        else:
+            g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
         out = g.group_host(heat_pin.numpy(), paf_pin.numpy(), H, params, out)
-        gather(0)
-    gather_join()
+        if sink is not None:
+            sink.publish(s, stream)
+            if rank == 0:
+                sink.collect(s, cstream)
+                sink.release(s, cstream)
+        elif pg is not None:
+            pg.gather()
+        return out
+
+    for _ in range(2):
+        out = host_call(out)
+    join_consumer()
     barrier()
     w0 = time.time()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = g.group_host(heat_pin.numpy(), paf_pin.numpy(), H, params, out)
-        gather(0)
-        gather_join()  # the next call overwrites handle 0's lists
+        out = host_call(out)
+    join_consumer()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     w1 = time.time()
@@ -316,6 +481,8 @@ def run_ours(args, rank, world, local_rank):
     d2h = world * sum(out[k].nbytes for k in ("n_persons", "people_xy", "people_score", "status"))
     clocks = sampler.stop() if sampler else None
 
+    if sink is not None:
+        sink.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,50 +495,54 @@ def run_ours(args, rank, world, local_rank):
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     names = list(g.stage_kernels())  # the kernel variants that actually ran (ncu names)
-    alg_bytes = [B * 18 * H * W * 4, B * 30 * H * W * 4, None, None]  # K1 reads heat once, K2a reads paf once
+    esz = 8 if args.paf == "f64" else 4
+    alg_bytes = [B * 18 * H * W * 4, B * 30 * H * W * esz, None, None]  # K1 reads heat once, K2a reads the body-part maps once
     kernels = {}
     for i, nme in enumerate(names):
-        kernels[nme] = {"ms": stage_ms[i], "algorithmic_GBps": (alg_bytes[i] / (stage_ms[i] * 1e-3) / 1e9) if alg_bytes[i] else None}
+        kernels[nme] = {"ms": stage_ms[i], "algorithmic_GBps": (alg_bytes[i] / (stage_ms[i] * 1e-3) / 1e9) if alg_bytes[i] else None,
+                        "frac_of_hbm_peak": (alg_bytes[i] / (stage_ms[i] * 1e-3) / 1e9 / hbm_peak) if alg_bytes[i] else None}
     if world > 1:
-        kernels["nccl_gather"] = {"ms": None, "algorithmic_GBps": None,
-                                  "note": "runs on a side stream out of the other handle's workspace, overlapped with the next step"}
+        kernels["gather"] = {"ms": stage_ms[4], "note": gather_how}
     dom = max(range(4), key=lambda i: stage_ms[i])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.config == "p30":
         traffic = json.load(open(tpath)).get(names[dom])
+    path_bytes = B * (18 * 4 + 30 * esz) * H * W
     if alg_bytes[dom]:
         ach = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes[dom]}
     else:
-        # a latency-bound kernel dominates: report the path's algorithmic bytes (3 145 728 B/image) over its time
-        ach = B * 48 * H * W * 4 / (stage_ms[dom] * 1e-3) / 1e9
+        ach = path_bytes / (stage_ms[dom] * 1e-3) / 1e9
         roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": B * 48 * H * W * 4,
+                    "algorithmic_bytes_per_launch": path_bytes,
                     "note": "serial, latency-bound kernel; bytes are the whole path's per-image figure x batch"}
-    # the north-star kernel always reported beside it
-    ls = kernels[names[1]]
-    roofline["limb_score_frac"] = ls["algorithmic_GBps"] / hbm_peak
+    roofline["limb_score_frac"] = kernels[names[1]]["frac_of_hbm_peak"]
+    roofline["nms_peaks_frac"] = kernels[names[0]]["frac_of_hbm_peak"]
+    ms_per_pass = elapsed_ms / n_pass
+    roofline["whole_path_frac"] = path_bytes / (ms_per_pass * 1e-3) / 1e9 / hbm_peak
 
     result = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 maps; f64 coordinates/scores", "data": "synthetic", "config": workload_config(args, world),
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "ms_per_pass": ms_per_pass, "timed_region_ms": elapsed_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{args.paf} body-part maps, f32 keypoint maps; f64 coordinates/scores", "data": "synthetic",
+        "config": workload_config(args, world, passes, gather_how),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "spg_group_host (C ABI, pinned host maps in, person lists out)"},
+                "steps": e2e_steps, "api": "spg_group_host (C ABI, pinned host maps in, person lists out); one call per step"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-        "kernel_timing": f"CUDA events around every kernel of every {stage_every}th step of the timed region ({len(evs)} of {args.steps} steps)",
-        "persons_found_per_image": float(r_np.mean()),
+        "kernel_timing": f"CUDA events around every kernel of {len(used)} passes inside the timed region ({n_pass} passes)",
+        "persons_found_per_image": float(r_np.mean()), "gather_verified": gather_ok,
     }
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import grouping_port as gp
         from oracle import spg_oracle as so
 
-        n_cpu = min(B, 256)
+        n_cpu = min(B, 256 if H * W <= 128 * 128 else 8)
         gp.group_image(heat_np[0], paf_np[0], H, params, skeleton.LIMBS)
         t0 = time.perf_counter()
         found = [gp.group_image(heat_np[i], paf_np[i], H, params, skeleton.LIMBS)[3].shape[0] for i in range(n_cpu)]
@@ -383,7 +554,7 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         so.group_batch(heat_np, paf_np, skeleton.LIMBS, H, params, threads=1)
         dt1 = time.perf_counter() - t0
-        nt = so.max_threads()
+        nt = min(so.max_threads(), host_cpu_budget()["usable"])
         t0 = time.perf_counter()
         so.group_batch(heat_np, paf_np, skeleton.LIMBS, H, params, threads=nt)
         dtn = time.perf_counter() - t0
@@ -401,13 +572,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if world == 1 and args.gpus > 1 and args.impl == "ours":
         raise SystemExit(f"--gpus {args.gpus} needs `python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...`")
-    import __graft_entry__ as ge
-
-    if rank == 0:
-        ge.build()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world)  # pure Python: builds and loads nothing of the product
     else:
+        build_once()
         run_ours(args, rank, world, local_rank)
 
 

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     const double *g_py = ws.peak_y + (size_t)n * K * capP;
     // wire record (include/spgroup.h): rows are staged in shared memory -- the connection tables are dead by now -- and
     // leave in one coalesced copy, so a record in a peer GPU's memory costs a few 128-byte NVLink writes per image
-    const int WR = 2 * J + 1;
+    const int WR = 2 * J + 2;  // x,y per joint, person score, presence mask
     const bool wire_on = ws.wire != nullptr && (size_t)min(ws.wire_rows, capR) * WR * sizeof(double) <= assemble_conn_bytes(L, capP);
     double *s_wire = reinterpret_cast<double *>(smem_raw);
     // keep flags first (reusing `touch`), then each kept row's output position = number of kept rows born earlier
@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         const double pscore = __dsub_rn(1.0, __ddiv_rn(1.0, total));  // :541
         g_score[o] = pscore;
         const bool wrow = wire_on && o < ws.wire_rows;
+        unsigned long long present = 0ull;
         if (wrow) s_wire[(size_t)o * WR + 2 * J] = pscore;
         for (int g = 0; g < J; g++) {                         // :523-539
             const int part = ws.out_from_part[g];
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
                 const int idx = id - t.off[part];
                 x = g_px[part * capP + idx];
                 y = g_py[part * capP + idx];
+                present |= 1ull << g;
             }
             g_xy[((size_t)o * J + g) * 2 + 0] = x;
             g_xy[((size_t)o * J + g) * 2 + 1] = y;
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
                 s_wire[(size_t)o * WR + 2 * g + 1] = y;
             }
         }
+        if (wrow) reinterpret_cast<unsigned long long *>(s_wire)[(size_t)o * WR + 2 * J + 1] = present;
     }
     if (ws.wire != nullptr && (!wire_on || out > ws.wire_rows)) flags |= kStWireOverflow;
     uint32_t st_word = 0;

@@ -386,7 +386,7 @@ int spg_get_device_view(const spg_handle *h, spg_device_view *v) {
 int64_t spg_wire_record_bytes(const spg_handle *h) {
     if (!h) return 0;
     const int rows = h->ws.wire_rows > 0 ? h->ws.wire_rows : h->ws.capR;
-    return 8 + (int64_t)rows * (2 * h->ws.J + 1) * (int64_t)sizeof(double);
+    return 8 + (int64_t)rows * (2 * h->ws.J + 2) * (int64_t)sizeof(double);
 }
 
 int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int32_t wire_rows) {
@@ -399,7 +399,7 @@ int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int
     if (wire_rows < 1 || wire_rows > h->ws.capR) return fail(h, SPG_E_INVALID, "wire_rows %d outside [1, max_person_rows=%d]", wire_rows, h->ws.capR);
     if (first_record < 0) return fail(h, SPG_E_INVALID, "first_record is negative");
     if ((reinterpret_cast<uintptr_t>(wire_dev) & 7) != 0) return fail(h, SPG_E_INVALID, "wire buffer must be 8-byte aligned");
-    if ((size_t)wire_rows * (2 * h->ws.J + 1) * sizeof(double) > assemble_conn_bytes(h->ws.L, h->ws.capP))
+    if ((size_t)wire_rows * (2 * h->ws.J + 2) * sizeof(double) > assemble_conn_bytes(h->ws.L, h->ws.capP))
         return fail(h, SPG_E_INVALID, "wire_rows %d do not fit the assemble kernel's staging area", wire_rows);
     h->ws.wire = static_cast<unsigned char *>(wire_dev);
     h->ws.wire_first = first_record;
@@ -612,22 +612,29 @@ int spg_upload_peaks(spg_handle *h, int32_t img, const int32_t *part_count, cons
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Workspace &ws = h->ws;
+    // the image's dense [K][capP] tables are laid out on the host and go up in three copies + the counters
+    const size_t KP = (size_t)ws.K * ws.capP;
+    std::vector<double> dx(KP, 0.0), dy(KP, 0.0);
+    std::vector<float> ds(KP, 0.0f);
     size_t off = 0;
     for (int c = 0; c < ws.K; c++) {
         const int m = part_count[c];
         if (m < 0 || m > ws.capP) return fail(h, SPG_E_INVALID, "part %d has %d peaks; capacity is %d", c, m, ws.capP);
-        const size_t dst = ((size_t)img * ws.K + c) * ws.capP;
-        if (m) {
-            if (!x || !y || !score) return fail(h, SPG_E_INVALID, "peak arrays are NULL");
-            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_x + dst, x + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_y + dst, y + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-            SPG_CUDA(h, cudaMemcpyAsync(ws.peak_score + dst, score + off, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+        if (m && (!x || !y || !score)) return fail(h, SPG_E_INVALID, "peak arrays are NULL");
+        for (int q = 0; q < m; q++) {
+            dx[(size_t)c * ws.capP + q] = x[off + q];
+            dy[(size_t)c * ws.capP + q] = y[off + q];
+            ds[(size_t)c * ws.capP + q] = score[off + q];
         }
         off += m;
     }
+    const size_t dst = (size_t)img * KP;
+    SPG_CUDA(h, cudaMemcpyAsync(ws.peak_x + dst, dx.data(), sizeof(double) * KP, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaMemcpyAsync(ws.peak_y + dst, dy.data(), sizeof(double) * KP, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaMemcpyAsync(ws.peak_score + dst, ds.data(), sizeof(float) * KP, cudaMemcpyHostToDevice, st));
     SPG_CUDA(h, cudaMemcpyAsync(ws.peak_count + (size_t)img * ws.K, part_count, sizeof(int32_t) * ws.K, cudaMemcpyHostToDevice, st));
     SPG_CUDA(h, cudaMemsetAsync(ws.status + img, 0, sizeof(uint32_t), st));
-    SPG_CUDA(h, cudaStreamSynchronize(st));  // the host arrays may be temporaries
+    SPG_CUDA(h, cudaStreamSynchronize(st));  // the host arrays are temporaries: one synchronisation per image
     h->stage = std::max(h->stage, 1);
     return SPG_OK;
 }
@@ -638,26 +645,30 @@ int spg_upload_connections(spg_handle *h, int32_t img, const int32_t *conn_count
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Workspace &ws = h->ws;
-    std::vector<uint32_t> packed;
+    // dense [L][capP] tables built on the host: three copies + the counters and ONE synchronisation per image
+    // (round 1 synchronised once per limb -- up to 30 host round trips per image)
+    const size_t LP = (size_t)ws.L * ws.capP;
+    std::vector<uint32_t> dij(LP, 0u);
+    std::vector<double> dsc(LP, 0.0), dnm(LP, 0.0);
     size_t off = 0;
     for (int k = 0; k < ws.L; k++) {
         const int m = conn_count[k];
         if (m > ws.capP) return fail(h, SPG_E_INVALID, "limb %d has %d connections; capacity is %d", k, m, ws.capP);
         if (m <= 0) continue;
         if (!ij || !score || !norm) return fail(h, SPG_E_INVALID, "connection arrays are NULL");
-        packed.resize(m);
         for (int r = 0; r < m; r++) {
             const int32_t i = ij[(off + r) * 2], j = ij[(off + r) * 2 + 1];
             if (i < 0 || j < 0 || i >= ws.capP || j >= ws.capP) return fail(h, SPG_E_INVALID, "connection index out of range");
-            packed[r] = ((uint32_t)i << 16) | (uint32_t)j;
+            dij[(size_t)k * ws.capP + r] = ((uint32_t)i << 16) | (uint32_t)j;
+            dsc[(size_t)k * ws.capP + r] = score[off + r];
+            dnm[(size_t)k * ws.capP + r] = norm[off + r];
         }
-        const size_t dst = ((size_t)img * ws.L + k) * ws.capP;
-        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_ij + dst, packed.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, st));
-        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_score + dst, score + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-        SPG_CUDA(h, cudaMemcpyAsync(ws.conn_norm + dst, norm + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-        SPG_CUDA(h, cudaStreamSynchronize(st));  // `packed` is reused
         off += m;
     }
+    const size_t dst = (size_t)img * LP;
+    SPG_CUDA(h, cudaMemcpyAsync(ws.conn_ij + dst, dij.data(), sizeof(uint32_t) * LP, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaMemcpyAsync(ws.conn_score + dst, dsc.data(), sizeof(double) * LP, cudaMemcpyHostToDevice, st));
+    SPG_CUDA(h, cudaMemcpyAsync(ws.conn_norm + dst, dnm.data(), sizeof(double) * LP, cudaMemcpyHostToDevice, st));
     SPG_CUDA(h, cudaMemcpyAsync(ws.conn_count + (size_t)img * ws.L, conn_count, sizeof(int32_t) * ws.L, cudaMemcpyHostToDevice, st));
     SPG_CUDA(h, cudaStreamSynchronize(st));
     h->stage = std::max(h->stage, 3);

@@ -23,34 +23,51 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .grouping import Grouper, GroupingError, GroupResult
-from .skeleton import COCO_FROM_PART, LIMBS, NUM_PARTS
+from .skeleton import COCO_FROM_PART, LIMBS, NUM_PARTS, GroupParams
 
 _limbs: Tuple[Tuple[int, int], ...] = LIMBS
 _device = 0
-_groupers: Dict[Tuple[int, int], Grouper] = {}
+_variant = "evaluate"
+_groupers: Dict[int, Grouper] = {}
 CAP_PEAKS, CAP_CANDS, CAP_ROWS = 128, 4096, 128
+MAX_DIM = 32767  # the C ABI's limit; the workspace does not depend on the map size, so ONE handle serves every image size
 
 
-def configure(limbs: Optional[Sequence[Tuple[int, int]]] = None, device: Optional[int] = None) -> None:
-    """Select the limb table (default: the Canonical ``limbs_conn``, config/config.py:94) and the CUDA device."""
-    global _limbs, _device
+def configure(limbs: Optional[Sequence[Tuple[int, int]]] = None, device: Optional[int] = None,
+              variant: Optional[str] = None) -> None:
+    """Select the limb table (default: the Canonical ``limbs_conn``, config/config.py:94), the CUDA device and the
+    behavioural variant: ``"evaluate"`` (evaluate.py, the default) or ``"demo"`` (demo_image.py's inlined copy, which
+    differs at :288, :414-415 and :533 -- SURVEY.md 3.2)."""
+    global _limbs, _device, _variant
     if limbs is not None:
         _limbs = tuple((int(a), int(b)) for a, b in limbs)
     if device is not None:
         _device = int(device)
+    if variant is not None:
+        if variant not in ("evaluate", "demo"):
+            raise ValueError("variant must be 'evaluate' or 'demo'")
+        _variant = variant
     for g in _groupers.values():
         g.close()
     _groupers.clear()
 
 
-def _grouper(H: int, W: int) -> Grouper:
-    key = (H, W)
-    g = _groupers.get(key)
+def _grouper(H: int = 0, W: int = 0) -> Grouper:
+    """The one native handle of the current device (evaluate.py runs over images of hundreds of different sizes: a
+    handle per size, as in round 1, grew device memory and streams without bound)."""
+    g = _groupers.get(_device)
     if g is None:
-        g = Grouper(_limbs, NUM_PARTS, COCO_FROM_PART, max_batch=1, max_h=H, max_w=W, max_peaks_per_part=CAP_PEAKS,
-                    max_cands_per_limb=CAP_CANDS, max_person_rows=CAP_ROWS, device=_device)
-        _groupers[key] = g
+        g = Grouper(_limbs, NUM_PARTS, COCO_FROM_PART, max_batch=1, max_h=MAX_DIM, max_w=MAX_DIM,
+                    max_peaks_per_part=CAP_PEAKS, max_cands_per_limb=CAP_CANDS, max_person_rows=CAP_ROWS, device=_device)
+        _groupers[_device] = g
     return g
+
+
+def _params(params):
+    """The reference's params dict -> what the library runs with (the demo variant adds its three deviations)."""
+    if isinstance(params, GroupParams):
+        return params
+    return GroupParams.demo(params) if _variant == "demo" else params
 
 
 def _check(r: GroupResult) -> None:
@@ -76,7 +93,7 @@ def find_peaks(heatmap_avg, params):
     """evaluate.py:169-203.  ``heatmap_avg [H,W,>=18]`` -> list[18] of [(x, y, score, id), ...]."""
     H, W = heatmap_avg.shape[:2]
     g = _grouper(H, W)
-    g.nms_peaks(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), params)  # the cast is evaluate.py:173
+    g.nms_peaks(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _params(params))  # the cast is evaluate.py:173
     r = g.fetch(1)
     _check(r)
     return r.as_reference_structures(0)[0]
@@ -88,8 +105,8 @@ def find_connections(all_peaks, paf_avg, image_width, params):
     g = _grouper(H, W)
     _upload_peaks(g, all_peaks)
     dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
-    g.limb_score(_maps_to_device(paf_avg, len(_limbs), dtype), image_width, params)
-    g.limb_match(1, params)
+    g.limb_score(_maps_to_device(paf_avg, len(_limbs), dtype), image_width, _params(params))
+    g.limb_match(1, _params(params))
     r = g.fetch(1)
     _check(r)
     # ids in the rows are those of the caller's all_peaks (:267), not positions in our tables
@@ -98,14 +115,14 @@ def find_connections(all_peaks, paf_avg, image_width, params):
         if isinstance(rows, list) or not len(rows):
             continue
         a, b = _limbs[k]
-        rows[:, 0] = [all_peaks[a][int(i)][3] for i in rows[:, 3]]
-        rows[:, 1] = [all_peaks[b][int(j)][3] for j in rows[:, 4]]
+        rows[:, 0] = np.array([t[3] for t in all_peaks[a]], np.float64)[rows[:, 3].astype(np.int64)]
+        rows[:, 1] = np.array([t[3] for t in all_peaks[b]], np.float64)[rows[:, 4].astype(np.int64)]
     return conns, special
 
 
 def find_people(connection_all, special_k, all_peaks, params):
     """evaluate.py:279-498 -> (subset [P,20,2] float64, candidate [N,4] float64)."""
-    g = next(iter(_groupers.values())) if _groupers else _grouper(128, 128)  # assembly does not depend on the map size
+    g = _grouper()  # assembly does not depend on the map size
     _upload_peaks(g, all_peaks)
     special = set(int(k) for k in special_k)
     counts, ij, sc, nm = [], [], [], []
@@ -120,7 +137,7 @@ def find_people(connection_all, special_k, all_peaks, params):
         nm.append(rows[:, 5])
     g.upload_connections(0, counts, np.concatenate(ij) if ij else np.zeros((0, 2), np.int32),
                          np.concatenate(sc) if sc else np.zeros(0), np.concatenate(nm) if nm else np.zeros(0))
-    g.assemble(1, params)
+    g.assemble(1, _params(params))
     r = g.fetch(1)
     _check(r)
     subset = r.subset[0, :int(r.n_persons[0])].copy()
@@ -143,7 +160,7 @@ def group(heatmap_avg, paf_avg, image_extent, params):
     g = _grouper(H, W)
     dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
     g.group_device(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _maps_to_device(paf_avg, len(_limbs), dtype),
-                   image_extent, params)
+                   image_extent, _params(params))
     r = g.fetch(1)
     _check(r)
     return r.as_reference_structures(0)
@@ -171,7 +188,7 @@ def keypoint_heatmap_nms(heat, kernel: int = 3, thre: float = 0.1):
     if heat.dim() != 4 or heat.shape[0] != 1:
         raise GroupingError("expected a [1,C,H,W] tensor")
     C, H, W = heat.shape[1:]
-    g = Grouper(((0, 0),), C, (0,), max_batch=1, max_h=H, max_w=W, max_peaks_per_part=CAP_PEAKS,
+    g = Grouper(((0, 0),), C, (0,), max_batch=1, max_h=MAX_DIM, max_w=MAX_DIM, max_peaks_per_part=CAP_PEAKS,
                 device=_device) if C != NUM_PARTS else _grouper(H, W)
     src = heat.to(f"cuda:{_device}", torch.float32).contiguous()
     g.nms_peaks(src, dict(thre1=float(thre), offset_radius=0))

@@ -188,6 +188,52 @@ class GroupResult:
         return [([tuple(xy) for xy in self.people_xy[n, j]], float(self.people_score[n, j])) for j in range(P)]
 
 
+# ---- peer memory + stream-ordered signalling (the NVLink gather; sharding.py drives it) ------------------------
+def wire_create(device: int, nbytes: int) -> Tuple[int, bytes]:
+    """Zero-filled device buffer other processes can map: ``(device address, 64-byte IPC handle)``."""
+    lib = load_library()
+    ptr, hd = C.c_void_p(), C.create_string_buffer(64)
+    if lib.spg_wire_create(C.c_int32(device), C.c_uint64(nbytes), C.byref(ptr), hd) != 0:
+        raise GroupingError("spg_wire_create failed: " + (lib.spg_last_error(None) or b"").decode())
+    return int(ptr.value), hd.raw
+
+
+def wire_open(device: int, ipc_handle: bytes) -> int:
+    lib = load_library()
+    ptr = C.c_void_p()
+    if lib.spg_wire_open(C.c_int32(device), C.c_char_p(ipc_handle), C.byref(ptr)) != 0:
+        raise GroupingError("spg_wire_open failed: " + (lib.spg_last_error(None) or b"").decode())
+    return int(ptr.value)
+
+
+def wire_close(peer_ptr: int) -> None:
+    load_library().spg_wire_close(C.c_void_p(peer_ptr))
+
+
+def wire_destroy(device: int, dev_ptr: int) -> None:
+    load_library().spg_wire_destroy(C.c_int32(device), C.c_void_p(dev_ptr))
+
+
+def wire_signal(device: int, word_ptr: int, value: int, stream) -> None:
+    """Release-store ``value`` into a 64-bit word (local or peer memory) after everything earlier on ``stream``."""
+    if load_library().spg_wire_signal(C.c_int32(device), C.c_void_p(word_ptr), C.c_uint64(value),
+                                      C.c_void_p(int(getattr(stream, "cuda_stream", stream)))) != 0:
+        raise GroupingError("spg_wire_signal failed")
+
+
+def wire_wait(device: int, word_ptr: int, value: int, stream) -> None:
+    """Make ``stream`` wait until the LOCAL 64-bit word is >= ``value`` (a stream memory operation, no SM involved)."""
+    if load_library().spg_wire_wait(C.c_int32(device), C.c_void_p(word_ptr), C.c_uint64(value),
+                                    C.c_void_p(int(getattr(stream, "cuda_stream", stream)))) != 0:
+        raise GroupingError("spg_wire_wait failed")
+
+
+def device_bytes_view(ptr: int, nbytes: int, device: int):
+    """Zero-copy uint8 torch view of raw device memory."""
+    import torch
+    return torch.as_tensor(_CudaView(ptr, (int(nbytes),), "|u1"), device=torch.device("cuda", device))
+
+
 class Grouper:
     """One native grouping handle.  Not thread-safe; use one per stream / GPU."""
 
@@ -243,13 +289,37 @@ class Grouper:
         """Names of the kernel variants the last launches used: (nms_peaks, limb_score, limb_match, assemble)."""
         return tuple((self._lib.spg_stage_kernel(self._h, i) or b"").decode() for i in range(4))
 
+    # -- wire records (include/spgroup.h; wire.py is the host-side view) -------------------------------
+    def wire_record_bytes(self, rows: Optional[int] = None) -> int:
+        """Bytes of one image's record with ``rows`` person rows (default: ``max_person_rows``)."""
+        return 8 + int(self.capR if rows is None else rows) * (2 * self.J + 2) * 8
+
+    def set_wire_output(self, dev_ptr: Optional[int], first_record: int = 0, rows: Optional[int] = None) -> None:
+        """Make the assemble stage also write one wire record per image to ``dev_ptr`` (a raw device address: local
+        memory or a peer GPU's buffer opened with ``wire_open``); ``None`` switches it off."""
+        rc = self._lib.spg_set_wire_output(self._h, C.c_void_p(dev_ptr or 0), C.c_int64(first_record),
+                                           C.c_int32(self.capR if rows is None else rows))
+        self._check(rc, "spg_set_wire_output")
+
     # -- helpers ---------------------------------------------------------------------------------
-    @staticmethod
-    def _stream_ptr(stream) -> C.c_void_p:
+    def _stream_ptr(self, stream) -> C.c_void_p:
         if stream is None:
             import torch
-            stream = torch.cuda.current_stream()
+            stream = torch.cuda.current_stream(self.device)  # the handle's device, not torch's current one
         return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+    def _check_maps(self, t, name: str, channels: int, dtypes) -> None:
+        """Shape / dtype / channel checks shared by the whole-path and the stage entry points."""
+        import torch
+        self._dev_tensor(t, name)
+        if t.device.index != self.device:
+            raise GroupingError(f"{name} lives on cuda:{t.device.index}, the handle on cuda:{self.device}")
+        if t.dtype not in dtypes:
+            raise GroupingError(f"{name} must be " + " or ".join(str(d).replace("torch.", "") for d in dtypes))
+        if t.shape[1] < channels:
+            raise GroupingError(f"{name} has {t.shape[1]} channels, the skeleton needs {channels}")
+        if t.shape[0] > self.max_batch:
+            raise GroupingError(f"{name} holds {t.shape[0]} images, the handle was created for {self.max_batch}")
 
     @staticmethod
     def _dev_tensor(t, name: str):
@@ -276,13 +346,11 @@ class Grouper:
         reference's ``oriImg.shape[0]`` (evaluate.py:510).
         """
         import torch
-        heat = self._dev_tensor(heat, "heat")
-        paf = self._dev_tensor(paf, "paf")
-        if heat.dtype != torch.float32:
-            raise GroupingError("heat must be float32 (find_peaks casts to float32, evaluate.py:173)")
+        self._check_maps(heat, "heat", self.K, (torch.float32,))  # find_peaks casts to float32, evaluate.py:173
+        self._check_maps(paf, "paf", self.L, (torch.float32, torch.float64))
         N, _, H, W = heat.shape
-        if paf.shape[0] != N or tuple(paf.shape[2:]) != (H, W) or heat.shape[1] < self.K or paf.shape[1] < self.L:
-            raise GroupingError("heat/paf shapes do not agree with the skeleton")
+        if paf.shape[0] != N or tuple(paf.shape[2:]) != (H, W):
+            raise GroupingError("heat/paf shapes do not agree")
         p = params_struct(params)
         rc = self._lib.spg_group_batch(self._h, C.c_void_p(heat.data_ptr()), C.c_int64(heat.stride(0)),
                                        C.c_int64(heat.stride(1)), C.c_void_p(paf.data_ptr()),
@@ -322,8 +390,10 @@ class Grouper:
     # -- stages -------------------------------------------------------------------------------------
     def nms_peaks(self, heat, params=None, stream=None) -> None:
         """find_peaks (evaluate.py:169-203) on ``heat [N,>=K,H,W]`` float32 CUDA."""
-        heat = self._dev_tensor(heat, "heat")
+        import torch
+        self._check_maps(heat, "heat", self.K, (torch.float32,))
         N, _, H, W = heat.shape
+        self._peaks_shape = (N, H, W)
         p = params_struct(params)
         rc = self._lib.spg_nms_peaks(self._h, C.c_void_p(heat.data_ptr()), C.c_int64(heat.stride(0)),
                                      C.c_int64(heat.stride(1)), C.c_int32(N), C.c_int32(H), C.c_int32(W), C.byref(p),
@@ -333,8 +403,12 @@ class Grouper:
 
     def limb_score(self, paf, image_extent: float, params=None, stream=None) -> None:
         """Scoring half of find_connections (evaluate.py:211-255) for peaks already on the device."""
-        paf = self._dev_tensor(paf, "paf")
+        import torch
+        self._check_maps(paf, "paf", self.L, (torch.float32, torch.float64))
         N, _, H, W = paf.shape
+        ps = getattr(self, "_peaks_shape", None)  # peaks from spg_nms_peaks: the maps must agree (uploaded peaks carry no shape)
+        if ps is not None and (ps[0] < N or ps[1:] != (H, W)):
+            raise GroupingError(f"paf is {N}x{H}x{W} but the peaks on the device come from {ps[0]}x{ps[1]}x{ps[2]} heat maps")
         p = params_struct(params)
         rc = self._lib.spg_limb_score(self._h, C.c_void_p(paf.data_ptr()), C.c_int32(self._paf_dtype(paf)),
                                       C.c_int64(paf.stride(0)), C.c_int64(paf.stride(1)), C.c_int32(N), C.c_int32(H),
@@ -356,6 +430,7 @@ class Grouper:
 
     # -- state transfer ---------------------------------------------------------------------------------
     def upload_peaks(self, image_index: int, part_count, x, y, score, stream=None) -> None:
+        self._peaks_shape = None
         pc = np.ascontiguousarray(part_count, np.int32)
         x = np.ascontiguousarray(x, np.float64)
         y = np.ascontiguousarray(y, np.float64)

@@ -81,7 +81,7 @@ def _put_limb(acc: np.ndarray, cnt: np.ndarray, xa, ya, xb, yb, sigma: float) ->
 
 def render(joints: np.ndarray, visible: np.ndarray, H: int, W: int, rng: np.random.Generator,
            limbs: Sequence[Tuple[int, int]] = LIMBS, noise: float = NOISE_MAX,
-           noise_levels: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+           noise_levels: Optional[int] = None, sigma_scale: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
     """Rasterise ``joints [P,18,2]`` (``visible [P,18]`` bool) into ``heat [18,H,W]`` and ``paf [L,H,W]``."""
     P = joints.shape[0]
     heat = np.zeros((NUM_PARTS, H, W), np.float32)
@@ -89,13 +89,13 @@ def render(joints: np.ndarray, visible: np.ndarray, H: int, W: int, rng: np.rand
     for p in range(P):
         for c in range(NUM_PARTS):
             if visible[p, c]:
-                _put_keypoint(heat[c], joints[p, c, 0], joints[p, c, 1], KEYPOINT_SIGMA)
+                _put_keypoint(heat[c], joints[p, c, 0], joints[p, c, 1], KEYPOINT_SIGMA * sigma_scale)
     cnt = np.zeros((H, W), np.int32)
     for k, (a, b) in enumerate(limbs):
         cnt[:] = 0
         for p in range(P):
             if visible[p, a] and visible[p, b]:
-                _put_limb(paf[k], cnt, joints[p, a, 0], joints[p, a, 1], joints[p, b, 0], joints[p, b, 1], LIMB_SIGMA)
+                _put_limb(paf[k], cnt, joints[p, a, 0], joints[p, a, 1], joints[p, b, 0], joints[p, b, 1], LIMB_SIGMA * sigma_scale)
         np.divide(paf[k], cnt, out=paf[k], where=cnt > 0)
     if noise > 0:
         for arr in (heat, paf):
@@ -113,7 +113,7 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
                limbs: Sequence[Tuple[int, int]] = LIMBS, drop_prob: float = 0.0, plateau: int = 0, spikes: int = 0,
                colocate: int = 0, missing_parts: Sequence[int] = (), edge: bool = False, negative_bias: float = 0.0,
                stretch: int = 0, noise_levels: Optional[int] = None, heat_gain: float = 1.0, paf_gain: float = 1.0,
-               scale_range: Tuple[float, float] = (0.8, 1.3)) -> Tuple[np.ndarray, np.ndarray]:
+               scale_range: Tuple[float, float] = (0.8, 1.3), sigma_scale: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
     """One synthetic image.  ``seed`` fully determines the result for a given numpy build.
 
     Dirty knobs: ``drop_prob`` removes joints at random; ``plateau`` copies that many peak values onto a
@@ -123,7 +123,8 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
     ``edge`` lets bodies leave the image (integer-coordinate border peaks, util.py:201-202);
     ``negative_bias`` shifts the body-part maps down so some samples are negative;
     ``stretch`` moves that many wrists far away (long-limb rejects, evaluate.py:324,353,409);
-    ``heat_gain`` / ``paf_gain`` scale the maps (weak persons that the final prune removes, :491-496).
+    ``heat_gain`` / ``paf_gain`` scale the maps (weak persons that the final prune removes, :491-496);
+    ``scale_range`` / ``sigma_scale`` size the bodies and the blobs (4x for maps at image resolution, stride 4).
     """
     rng = np.random.default_rng(seed)
     joints = sample_skeletons(rng, persons, H, W, edge=edge, scale_range=scale_range)
@@ -144,7 +145,7 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
         c = int(rng.choice([4, 7, 10, 13]))
         joints[p, c, 0] = rng.uniform(4, W - 5)
         joints[p, c, 1] = rng.uniform(4, H - 5)
-    heat, paf = render(joints, visible, H, W, rng, limbs=limbs, noise_levels=noise_levels)
+    heat, paf = render(joints, visible, H, W, rng, limbs=limbs, noise_levels=noise_levels, sigma_scale=sigma_scale)
     for _ in range(spikes):
         c, y, x = int(rng.integers(NUM_PARTS)), int(rng.integers(H)), int(rng.integers(W))
         heat[c, y, x] = max(heat[c, y, x], np.float32(rng.uniform(0.12, 0.6)))

@@ -166,16 +166,18 @@ int spg_download_people(spg_handle *h, int32_t n_images, int32_t *n_persons /*[N
 int spg_download_status(spg_handle *h, int32_t n_images, uint32_t *status /*[N]*/, void *stream);
 
 /* ---- wire records: what leaves the GPU (format_results, evaluate.py:563-582) ------------------------------- */
-/* One fixed-stride record per image: an 8-byte header followed by `rows` person rows of (2*n_out_joints + 1)
- * doubles -- x0,y0,...,x16,y16 in COCO order (evaluate.py:523-539), then the person score 1 - 1/total (:541) --
- * i.e. exactly the payload format_results turns into {"keypoints": [x,y,v]*17, "score": s} (v = x>0 or y>0).
+/* One fixed-stride record per image: an 8-byte header followed by `rows` person rows of (2*n_out_joints + 2)
+ * 8-byte words -- x0,y0,...,x16,y16 (doubles, COCO order, evaluate.py:523-539), the person score 1 - 1/total
+ * (double, :541), and a uint64 presence mask (bit g set: joint g was found; clear: the reference's `X, Y = 0, 0`
+ * placeholder, :531) -- i.e. exactly the payload format_results turns into {"keypoints": [x,y,v]*17, "score": s}
+ * (v = x>0 or y>0).
  * Only the first n_persons rows are written; the rest of the slot is never touched, so when the record lives in
  * another GPU's memory only live rows cross NVLink. */
 typedef struct spg_wire_header {
     int32_t n_persons;
     uint32_t status; /* SPG_ST_* bits of the image */
 } spg_wire_header;
-/* bytes of one image's record for this handle: 8 + wire_rows * (2*n_out_joints + 1) * 8 */
+/* bytes of one image's record for this handle: 8 + wire_rows * (2*n_out_joints + 2) * 8 */
 int64_t spg_wire_record_bytes(const spg_handle *h);
 /* Direct the assemble stage to ALSO emit wire records: image i of a call goes to
  * (char*)wire_dev + (first_record + i) * spg_wire_record_bytes().  `wire_dev` may be local device memory or PEER

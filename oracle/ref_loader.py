@@ -111,6 +111,20 @@ class Reference:
         return peaks, conns, special, subset, candidate
 
 
+def reference_function(name: str, extra_globals: dict = None):
+    """Any top-level function of /root/reference/evaluate.py, lifted verbatim (e.g. ``format_results`` :563-582)."""
+    import json
+
+    import numpy as np
+
+    src = open(os.path.join(REFERENCE_ROOT, "evaluate.py"), encoding="utf-8").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np, "math": math, "json": json, "os": os}
+    ns.update(extra_globals or {})
+    exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REFERENCE_ROOT, "evaluate.py"), "exec"), ns)
+    return ns[name]
+
+
 class DemoReference:
     """The grouping code INLINED in ``demo_image.py``'s ``process()`` (``/root/reference/demo_image.py:185-536``), lifted
     statement for statement: everything from ``all_peaks = []`` (:185) to the final prune

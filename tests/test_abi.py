@@ -105,3 +105,18 @@ def test_synth_is_seed_deterministic_and_shaped():
     assert a[0].shape == (18, 64, 80) and a[1].shape == (30, 64, 80)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert a[0].max() <= 1.0 and a[0].min() >= 0.0
+
+
+def test_shipped_library_has_no_result_changing_debug_switch():
+    """SPG_DEBUG_PERSIST must not exist in the default build; the tuning switches that remain are
+    read once in spg_create."""
+    from improved_body_parts_b200 import grouping
+    blob = open(grouping.LIB_PATH, "rb").read()
+    assert b"SPG_DEBUG" not in blob
+    for name in (b"SPG_PERSIST", b"SPG_NO_SCREEN", b"SPG_EXACT_WARPS"):
+        assert name in blob
+    src = open(os.path.join(ROOT, "improved_body_parts_b200", "csrc", "spgroup.cu")).read()
+    body = src.split("int spg_create(")[1].split("\nvoid spg_destroy")[0]
+    outside = src.replace(body, "")
+    assert body.count("getenv(") >= 3
+    assert outside.count("getenv(") == 1 and "#ifdef SPG_DEBUG" in outside  # the one left is compiled out of the shipped build
