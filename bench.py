@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: packed NCCL gather instead of NVLink peer stores")
+    ap.add_argument("--unfused", action="store_true", help="limb_match and assemble as two kernels instead of the fused match_assemble")
     ap.add_argument("--unmodified", action="store_true",
                     help="--impl reference only, build container only: time the UNMODIFIED reference functions (oracle/ref_loader)")
     args = ap.parse_args()
@@ -272,6 +273,8 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the grouping path has no CPU fallback")
+    if args.unfused:
+        os.environ["SPG_FUSE_MA"] = "0"  # read once at spg_create: the host entry point then runs the two kernels too
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -305,6 +308,9 @@ def run_ours(args, rank, world, local_rank):
             gather_how = gather_how or "one packed NCCL gather per pass (pre-allocated buffers)"
     cstream = torch.cuda.Stream(device=dev) if (sink is not None and rank == 0) else None
     pass_no = [0]
+    stages = [lambda: g.nms_peaks(heat_d, params), lambda: g.limb_score(paf_d, H, params)]
+    stages += [lambda: g.limb_match(B, params), lambda: g.assemble(B, params)] if args.unfused else [lambda: g.match_assemble(B, params)]
+    n_stage = len(stages)
 
     def one_pass(evs=None):
         s = pass_no[0]
@@ -315,15 +321,10 @@ def run_ours(args, rank, world, local_rank):
             g.set_wire_output(pg.local.data_ptr(), 0, CAP_ROWS)
         else:
             g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
-        if evs: evs[0].record(stream)
-        g.nms_peaks(heat_d, params)
-        if evs: evs[1].record(stream)
-        g.limb_score(paf_d, H, params)
-        if evs: evs[2].record(stream)
-        g.limb_match(B, params)
-        if evs: evs[3].record(stream)
-        g.assemble(B, params)
-        if evs: evs[4].record(stream)
+        for i, fn in enumerate(stages):
+            if evs: evs[i].record(stream)
+            fn()
+        if evs: evs[n_stage].record(stream)
         if sink is not None:
             sink.publish(s, stream)
             if rank == 0:  # the consumer: waits for every rank's counters (stream memory ops), then frees the generation
@@ -331,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
                 sink.release(s, cstream)
         elif pg is not None:
             pg.gather()
-        if evs: evs[5].record(stream)
+        if evs: evs[n_stage + 1].record(stream)
 
     def join_consumer():
         if cstream is not None:
@@ -349,7 +350,7 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.start()
 
-    n_ev = 6
+    n_ev = n_stage + 2
     for _ in range(3):
         one_pass()
     join_consumer()
@@ -408,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
     assert (r_status == 0).all(), f"status flags set: {np.unique(r_status)}"
     assert r_np.min() > 0, "no persons found -- the timed path did no work"
     g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
-    g.assemble(B, params)
+    stages[-1]()
     torch.cuda.synchronize()
     mine = local_wire.cpu().numpy()
     rec = wire.as_records(mine, 17, CAP_ROWS)
@@ -494,16 +495,16 @@ def run_ours(args, rank, world, local_rank):
         hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    names = list(g.stage_kernels())  # the kernel variants that actually ran (ncu names)
+    names = [nme for nme in g.stage_kernels() if nme][:n_stage]  # the kernel variants that actually ran (ncu names)
     esz = 8 if args.paf == "f64" else 4
-    alg_bytes = [B * 18 * H * W * 4, B * 30 * H * W * esz, None, None]  # K1 reads heat once, K2a reads the body-part maps once
+    alg_bytes = [B * 18 * H * W * 4, B * 30 * H * W * esz, None, None][:n_stage]  # K1 reads heat once, K2a reads the body-part maps once
     kernels = {}
     for i, nme in enumerate(names):
         kernels[nme] = {"ms": stage_ms[i], "algorithmic_GBps": (alg_bytes[i] / (stage_ms[i] * 1e-3) / 1e9) if alg_bytes[i] else None,
                         "frac_of_hbm_peak": (alg_bytes[i] / (stage_ms[i] * 1e-3) / 1e9 / hbm_peak) if alg_bytes[i] else None}
     if world > 1:
-        kernels["gather"] = {"ms": stage_ms[4], "note": gather_how}
-    dom = max(range(4), key=lambda i: stage_ms[i])
+        kernels["gather"] = {"ms": stage_ms[n_stage], "note": gather_how}
+    dom = max(range(n_stage), key=lambda i: stage_ms[i])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and args.config == "p30":

@@ -176,16 +176,17 @@ __device__ __forceinline__ uint32_t apply_connection(const PersonTable &t, const
 
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-__global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// One warp assembles one image.  FUSED = false: the stand-alone kernel -- the image's connection tables are fetched
+// from global memory up front.  FUSED = true: the match+assemble kernel -- matcher warps of the same CTA write each
+// limb's rows straight into the shared-memory tables and raise s_ready[k]; the assembler acquires limb k's flag right
+// before it consumes the limb, so matching limbs k+1.. overlaps assembling limb k.
+template <bool FUSED>
+__device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned char *smem_raw, uint64_t &bar, int n, int img_in_call,
+                                               int lane, const int *s_ready) {
     const Workspace &ws = a.ws;
-    const int lane = threadIdx.x;
-    if ((int)blockIdx.x >= a.n_images) return;
-    const int n = a.image_base + blockIdx.x;
     const int K = ws.K, L = ws.L, capP = ws.capP, capR = ws.capR;
 
     // shared memory: [conn_score | conn_norm | conn_ij | conn_count] of this image, then the person table
-    __shared__ uint64_t bar;
     const size_t LC = (size_t)L * capP;
     double *s_cs = reinterpret_cast<double *>(smem_raw);
     double *s_cn = s_cs + LC;
@@ -211,7 +212,9 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     // Everything this image needs from global memory is fetched up front -- the connection tables by the bulk-copy
     // engine -- so that the serial limb loop below never waits on L2.
     const size_t img_conn = (size_t)n * LC;
-    if (a.use_bulk) {
+    if (FUSED) {
+        // the matcher warps fill the tables
+    } else if (a.use_bulk) {
         if (lane == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
@@ -227,7 +230,8 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
             s_cij[i] = ws.conn_ij[img_conn + i];
         }
     }
-    for (int k = lane; k < L; k += 32) s_cc[k] = ws.conn_count[(size_t)n * L + k];
+    if (!FUSED)
+        for (int k = lane; k < L; k += 32) s_cc[k] = ws.conn_count[(size_t)n * L + k];
     if (lane == 0) {
         int acc = 0;
         for (int c = 0; c < K; c++) {
@@ -245,13 +249,20 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         t.alive[i] = 0;
     }
     __syncwarp();
-    if (a.use_bulk) mbar_wait(&bar, 0);
+    if (!FUSED && a.use_bulk) mbar_wait(&bar, 0);
 
     int nrows = 0;
     uint32_t flags = 0;
     bool overflow = false;
 
     for (int k = 0; k < L && !overflow; k++) {
+        if (FUSED) {  // acquire: limb k's rows and counter are in shared memory
+            int r;
+            do {
+                asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(r) : "r"(smem_u32(s_ready + k)) : "memory");
+                if (!r) __nanosleep(20);
+            } while (!r);
+        }
         const int cc = s_cc[k];
         if (cc < 0) continue;  // special_k (:290)
         const int A = ws.limbs[2 * k], B = ws.limbs[2 * k + 1];
@@ -293,6 +304,15 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
                 pending &= ~emask;
                 __syncwarp();
             }
+        }
+    }
+    if (FUSED && overflow) {  // the matchers may still be writing the tables this warp is about to reuse as staging space
+        for (int k = 0; k < L; k++) {
+            int r;
+            do {
+                asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(r) : "r"(smem_u32(s_ready + k)) : "memory");
+                if (!r) __nanosleep(20);
+            } while (!r);
         }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
@@ -371,7 +391,7 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
     if (ws.wire != nullptr) {
         __syncwarp();
         const size_t rec_bytes = 8 + (size_t)ws.wire_rows * WR * sizeof(double);
-        unsigned char *rec = ws.wire + (size_t)(ws.wire_first + (long long)blockIdx.x) * rec_bytes;
+        unsigned char *rec = ws.wire + (size_t)(ws.wire_first + (long long)img_in_call) * rec_bytes;
         const int wn = wire_on ? min(out, ws.wire_rows) : 0;
         if (lane == 0) {
             reinterpret_cast<int *>(rec)[0] = wn;
@@ -380,6 +400,13 @@ __global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs
         double *rows = reinterpret_cast<double *>(rec + 8);
         for (int i = lane; i < wn * WR; i += 32) rows[i] = s_wire[i];
     }
+}
+
+__global__ void __launch_bounds__(kAssembleThreads) assemble_kernel(AssembleArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    if ((int)blockIdx.x >= a.n_images) return;
+    assemble_image<false>(a, smem_raw, bar, a.image_base + blockIdx.x, blockIdx.x, threadIdx.x, nullptr);
 }
 
 }  // namespace spg

@@ -44,8 +44,8 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
 // number of register slots so that limbs with few survivors do not pay for eight.  The accepted row's (i, j)
 // and score are stored by the lane that owns the winner; limb lengths are filled in afterwards in parallel.
 template <int NS>
-__device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsigned long long (&key8)[kMatchRegCands],
-                                                 size_t obase, int nC, int lim, int lane) {
+__device__ __forceinline__ int match_rounds_keys(uint32_t *o_ij, double *o_norm, const unsigned long long (&key8)[kMatchRegCands],
+                                                 int nC, int lim, int lane) {
     unsigned long long key[NS];  // 0 = dead / absent
 #pragma unroll
     for (int r = 0; r < NS; r++) key[r] = (lane + 32 * r < nC) ? key8[r] : 0ull;  // loaded speculatively, before nC was known
@@ -64,8 +64,8 @@ __device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsi
 #pragma unroll
             for (int r = 1; r < NS; r++)
                 if (key[r] == best) wr = r;
-            ws.conn_ij[obase + m] = wij;  // row [idA, idB, score, i, j, norm] (evaluate.py:267); score and norm follow below
-            reinterpret_cast<int *>(ws.conn_norm + obase + m)[0] = lane + 32 * wr;  // candidate index, replaced by the norm
+            o_ij[m] = wij;  // row [idA, idB, score, i, j, norm] (evaluate.py:267); score and norm follow below
+            reinterpret_cast<int *>(o_norm + m)[0] = lane + 32 * wr;  // candidate index, replaced by the norm
         }
         // strike everything that shares an end point with the winner (including the winner itself)
 #pragma unroll
@@ -78,13 +78,11 @@ __device__ __forceinline__ int match_rounds_keys(const Workspace &ws, const unsi
     return m;
 }
 
-__global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) {
-    const Workspace &ws = a.ws;
-    const int lane = threadIdx.x & 31;
-    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    if (w >= a.n_images * ws.L) return;
-    const int k = w % ws.L;
-    const int n = a.image_base + w / ws.L;
+// The greedy matching of ONE (image, limb) by one warp.  Rows go to o_ij / o_score / o_norm (global memory in the
+// stand-alone kernel, shared memory in the fused match+assemble kernel); returns the number of connections, -1 for
+// special_k (evaluate.py:272-274).
+__device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int lane, bool keys_valid, uint32_t *o_ij,
+                                          double *o_score, double *o_norm) {
     const size_t slot = (size_t)n * ws.L + k;
     const size_t cbase = slot * ws.capC;
     const int pa = ws.limbs[2 * k], pb = ws.limbs[2 * k + 1];
@@ -94,55 +92,51 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
 #pragma unroll
     for (int r = 0; r < kMatchRegCands; r++) {
         const int cidx = lane + 32 * r;
-        key8[r] = (a.keys_valid && cidx < ws.capC) ? ws.cand_key[cbase + cidx] : 0ull;
+        key8[r] = (keys_valid && cidx < ws.capC) ? ws.cand_key[cbase + cidx] : 0ull;
     }
     const int nC = ws.cand_count[slot];
     const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
-    if (nC < 0) {  // special_k
-        if (lane == 0) ws.conn_count[slot] = -1;
-        return;
-    }
+    if (nC < 0) return -1;  // special_k
     const int nA = min(cntA, ws.capP);
     const int nB = min(cntB, ws.capP);
     const int lim = min(nA, nB);
-    const size_t obase = slot * ws.capP;
     const size_t baseA = ((size_t)n * ws.K + pa) * ws.capP, baseB = ((size_t)n * ws.K + pb) * ws.capP;
 
     auto emit = [&](int m, uint32_t ij, int cidx) {  // row [idA, idB, score, i, j, norm] (evaluate.py:267)
         const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
         const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
         const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
-        ws.conn_ij[obase + m] = ij;
-        ws.conn_score[obase + m] = ws.cand_score[cbase + cidx];
-        ws.conn_norm[obase + m] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+        o_ij[m] = ij;
+        o_score[m] = ws.cand_score[cbase + cidx];
+        o_norm[m] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
     };
 
     int m = 0;
     const int nslots = (nC + 31) >> 5;
-    if (a.keys_valid && nC <= 32 * kMatchRegCands) {
+    if (keys_valid && nC <= 32 * kMatchRegCands) {
         // ---- fast path, f32 planes: one 64-bit key per survivor, all in registers -----------------------
         switch (nslots) {
             case 0: break;
-            case 1: m = match_rounds_keys<1>(ws, key8, obase, nC, lim, lane); break;
-            case 2: m = match_rounds_keys<2>(ws, key8, obase, nC, lim, lane); break;
-            case 3: m = match_rounds_keys<3>(ws, key8, obase, nC, lim, lane); break;
-            case 4: m = match_rounds_keys<4>(ws, key8, obase, nC, lim, lane); break;
-            case 5: m = match_rounds_keys<5>(ws, key8, obase, nC, lim, lane); break;
-            case 6: m = match_rounds_keys<6>(ws, key8, obase, nC, lim, lane); break;
-            case 7: m = match_rounds_keys<7>(ws, key8, obase, nC, lim, lane); break;
-            case 8: m = match_rounds_keys<8>(ws, key8, obase, nC, lim, lane); break;
-            case 9: case 10: m = match_rounds_keys<10>(ws, key8, obase, nC, lim, lane); break;
-            case 11: case 12: m = match_rounds_keys<12>(ws, key8, obase, nC, lim, lane); break;
-            default: m = match_rounds_keys<16>(ws, key8, obase, nC, lim, lane); break;
+            case 1: m = match_rounds_keys<1>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 2: m = match_rounds_keys<2>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 3: m = match_rounds_keys<3>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 4: m = match_rounds_keys<4>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 5: m = match_rounds_keys<5>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 6: m = match_rounds_keys<6>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 7: m = match_rounds_keys<7>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 8: m = match_rounds_keys<8>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 9: case 10: m = match_rounds_keys<10>(o_ij, o_norm, key8, nC, lim, lane); break;
+            case 11: case 12: m = match_rounds_keys<12>(o_ij, o_norm, key8, nC, lim, lane); break;
+            default: m = match_rounds_keys<16>(o_ij, o_norm, key8, nC, lim, lane); break;
         }
         __syncwarp();  // the rows were written by different lanes of this warp
         for (int c = lane; c < m; c += 32) {  // scores and limb lengths (the reference's `norm`, :225) in parallel
-            const uint32_t ij = ws.conn_ij[obase + c];
-            ws.conn_score[obase + c] = ws.cand_score[cbase + reinterpret_cast<const int *>(ws.conn_norm + obase + c)[0]];
+            const uint32_t ij = o_ij[c];
+            o_score[c] = ws.cand_score[cbase + reinterpret_cast<const int *>(o_norm + c)[0]];
             const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
             const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
             const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
-            ws.conn_norm[obase + c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+            o_norm[c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
         }
     } else if (nC <= 32 * kMatchRegF64) {
         // ---- register path, f64 planes: (ordered f64 priority, tie-break) -------------------------------
@@ -213,6 +207,19 @@ __global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) 
             m++;
         }
     }
+    return m;
+}
+
+__global__ void __launch_bounds__(kMatchThreads) limb_match_kernel(MatchArgs a) {
+    const Workspace &ws = a.ws;
+    const int lane = threadIdx.x & 31;
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (w >= a.n_images * ws.L) return;
+    const int k = w % ws.L;
+    const int n = a.image_base + w / ws.L;
+    const size_t slot = (size_t)n * ws.L + k;
+    const size_t obase = slot * ws.capP;
+    const int m = match_limb(ws, n, k, lane, a.keys_valid != 0, ws.conn_ij + obase, ws.conn_score + obase, ws.conn_norm + obase);
     if (lane == 0) ws.conn_count[slot] = m;
 }
 

@@ -39,6 +39,7 @@ struct ScoreArgs {
     int debug;                                       // only read in -DSPG_DEBUG builds (timing experiments); always 0 otherwise
     int crit1_strict;                                // demo_image.py:288 compares with `>` where evaluate.py:246 uses `>=`
     int exact_warps;                                 // persistent kernel: scorer warps (the rest screen)
+    int wait_ns;                                     // persistent kernel: back-off of the role hand-off waits (0 = hint wait)
     double image_extent, thre2, connect_ration;
     Workspace ws;
 };
@@ -66,9 +67,11 @@ struct PairGeom {  // one limb's end-point lists in shared memory
 
 // Phase B: the reference's evaluation of one pair (evaluate.py:224-255).  Returns true if it is a candidate.
 // kExactBatch: samples of the exact evaluation whose index computations and loads are in flight together (register budget)
-template <typename T, int kExactBatch = 1>
+// T: the type the plane is STORED in; TA: the type the reference's arithmetic runs in (TA = double with T = float is
+// SPG_F32_AS_F64: float64 maps whose values are exact float32 numbers, the single-scale output of predict()).
+template <typename T, int kExactBatch = 1, typename TA = T>
 __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, int H, int W, const ScoreArgs &a,
-                                                 const PairGeom &g, int i, int j, bool interior, T thre2,
+                                                 const PairGeom &g, int i, int j, bool interior, TA thre2,
                                                  double &score, double &prio, bool &bad) {
     const double ax = g.ax[i], ay = g.ay[i], bx = g.bx[j], by = g.by[j];
     const double vx = __dsub_rn(bx, ax), vy = __dsub_rn(by, ay);                            // :224
@@ -103,7 +106,7 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
             stepy = __ddiv_rn(vy, dd);
         }
     }
-    T sum = (T)0;
+    TA sum = (TA)0;
     int above = 0;
     if (interior) {
         // both end points lie inside the map ([0, W-1] x [0, H-1]) and the samples stay between them (to within an
@@ -118,7 +121,7 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
                 // (a DADD instead of F2I.F64 on the quarter-rate conversion pipe)
                 const int xi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(td, stepx), ax), 6755399441055744.0));
                 const int yi = __double2loint(__dadd_rn(__dadd_rn(__dmul_rn(td, stepy), ay), 6755399441055744.0));
-                const T v = plane[yi * W + xi];
+                const TA v = (TA)plane[yi * W + xi];
                 sum = sum + v;  // sequential, in sample order, in the plane's precision (:241)
                 above += v > thre2;
                 td = __dadd_rn(td, 1.0);
@@ -139,15 +142,15 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
 #pragma unroll
                 for (int u = 0; u < kExactBatch; u++) {
                     if (t0 + u < last) {
-                        sum = sum + vv[u];  // sequential, in sample order, in the plane's precision (:241)
-                        above += vv[u] > thre2;
+                        sum = sum + (TA)vv[u];  // sequential, in sample order, in the plane's precision (:241)
+                        above += (TA)vv[u] > thre2;
                     }
                 }
                 td = __dadd_rn(td, (double)kExactBatch);
             }
         }
-        const T v = m > 1 ? plane[__double2int_rn(by) * W + __double2int_rn(bx)]
-                          : plane[__double2int_rn(ay) * W + __double2int_rn(ax)];
+        const TA v = (TA)(m > 1 ? plane[__double2int_rn(by) * W + __double2int_rn(bx)]
+                               : plane[__double2int_rn(ay) * W + __double2int_rn(ax)]);
         sum = sum + v;
         above += v > thre2;
     } else {
@@ -167,7 +170,7 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
                 bad = true;
                 return false;
             }
-            const T v = plane[(size_t)yi * W + xi];
+            const TA v = (TA)plane[(size_t)yi * W + xi];
             sum = sum + v;
             above += v > thre2;
         }
@@ -175,7 +178,7 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
     // :241 -- `image_width` is the image HEIGHT at the call site (:510)
     double prior = 0.0;  // only its value when negative matters: min(prior, 0)
     if (need_norm && norm > half) prior = __dsub_rn(__ddiv_rn(half, norm), 1.0);
-    if (sizeof(T) == 4) {
+    if (sizeof(TA) == 4) {
         float s = __fdiv_rn((float)sum, (float)m);
         s = __fadd_rn(s, prior < 0.0 ? __double2float_rn(prior) : 0.0f);  // f32 + weak Python float
         const float pr = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, s), __fmul_rn(0.25f, g.as[i])), __fmul_rn(0.25f, g.bs[j]));
@@ -192,7 +195,15 @@ __device__ __forceinline__ bool score_pair_exact(const T *__restrict__ plane, in
     return crit1 && crit2;
 }
 
-template <typename T, bool STAGE>
+// largest float32 <= t: for float32-stored values v, (double)v > t  <=>  v > screen_threshold(t) -- lets the float32
+// screen apply the float64 comparison of SPG_F32_AS_F64 exactly
+__host__ __device__ inline float f32_not_above(double t) {
+    float f = (float)t;
+    if ((double)f > t) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+template <typename T, bool STAGE, typename TA = T>
 __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -307,7 +318,9 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
     __syncthreads();
     if (STAGE) mbar_wait(&bar, 0);
     const T *plane = STAGE ? reinterpret_cast<const T *>(smem_raw) : gplane;
-    const T thre2 = (T)a.thre2;  // f32 plane: `> thre2` is an f32 compare against (float)thre2
+    // f32 plane: `> thre2` is an f32 compare against (float)thre2; f64 arithmetic on f32 storage: the equivalent f32 threshold
+    const T thre2 = (sizeof(T) == 4 && sizeof(TA) == 8) ? (T)f32_not_above(a.thre2) : (T)a.thre2;
+    const TA thre2_exact = (TA)a.thre2;
 
     // ---------------- phase A: conservative screen ----------------
     const uint32_t magic = s_magic;  // p / nB == umulhi(p, magic) for p < 2^14
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
         const int j = p - i * nB;
         double score, prio;
         bool bad = false;
-        const bool ok = score_pair_exact<T>(plane, H, W, a, g, i, j, s_ain[i] && s_bin[j], thre2, score, prio, bad);
+        const bool ok = score_pair_exact<T, 1, TA>(plane, H, W, a, g, i, j, s_ain[i] && s_bin[j], thre2_exact, score, prio, bad);
         if (bad) atomicOr(&s_flags, kStSampleIndex);
         if (ok) {
             const int pos = atomicAdd(&s_count, 1);  // warp-aggregated by ptxas (REDUX + one ATOMS)
@@ -403,7 +416,7 @@ __global__ void __launch_bounds__(kScoreThreads, 3) limb_score_kernel(ScoreArgs 
                 ws.cand_score[out_base + pos] = score;
                 const uint32_t ij = ((uint32_t)i << 16) | (uint32_t)j;
                 ws.cand_ij[out_base + pos] = ij;
-                if (sizeof(T) == 4) {  // the priority is an f32 value: 32 order-preserving bits + the tie-break fit one word
+                if (sizeof(TA) == 4) {  // the priority is an f32 value: 32 order-preserving bits + the tie-break fit one word
                     const uint32_t b = __float_as_uint((float)prio);
                     const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
                     ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);

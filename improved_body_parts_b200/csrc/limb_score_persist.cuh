@@ -168,6 +168,7 @@ __device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool val
     maxfail += qmax - qn;
 }
 
+template <typename TA>  // float: f32 planes, f32 arithmetic; double: f32 planes evaluated in float64 (SPG_F32_AS_F64)
 __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // full: plane copy landed + lists published; screened: every screener has left the item -- its survivor list is
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
     const int G = gridDim.x;
     const int nj = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / G + 1 : 0;
     const bool screen = a.screen && a.mid_num <= kScreenMaxMid && H <= kScreenMaxDim && W <= kScreenMaxDim;
-    const T thre2 = (T)a.thre2;
+    const T thre2 = sizeof(TA) == 8 ? f32_not_above(a.thre2) : (T)a.thre2;  // the screen's float32 threshold
+    const TA thre2_exact = (TA)a.thre2;
     auto plane_of = [&](int n_local, int k) {
         return reinterpret_cast<const T *>(a.paf) + (int64_t)n_local * a.img_stride + (int64_t)k * a.chan_stride;
     };
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             const int s = j % kPersistSlots, e = j % kMetaSlots;
             if (j >= kPersistSlots) {  // the plane slot's previous item has been screened
                 const int jp = j - kPersistSlots;
-                mbar_wait_sleep(&bar_screened[jp % kMetaSlots], (jp / kMetaSlots) & 1);
+                mbar_wait_tuned(&bar_screened[jp % kMetaSlots], (jp / kMetaSlots) & 1, a.wait_ns);
             }
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / L, k = item - n_local * L;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 }
             }
             if (j >= kMetaSlots) {
-                mbar_wait_sleep(&bar_mfree[e], ((j / kMetaSlots) - 1) & 1);
+                mbar_wait_tuned(&bar_mfree[e], ((j / kMetaSlots) - 1) & 1, a.wait_ns);
                 close_item(j - kMetaSlots);
             }
             MetaSlot &ms = s_meta[e];
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             if (j + 1 < nj) fetch(j + 1);              // in flight while the next iteration waits for its slots
         }
         for (int jp = max(0, nj - kMetaSlots); jp < nj; jp++) {  // the items still in the meta ring
-            mbar_wait_sleep(&bar_mfree[jp % kMetaSlots], (jp / kMetaSlots) & 1);
+            mbar_wait_tuned(&bar_mfree[jp % kMetaSlots], (jp / kMetaSlots) & 1, a.wait_ns);
             close_item(jp);
         }
     } else {
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             PairGeom g{ps.ax, ps.ay, ps.bx, ps.by, ps.as, ps.bs, s_rcp};
             double score, prio;
             bool bad = false;
-            const bool ok = score_pair_exact<T, 10>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2, score, prio, bad);
+            const bool ok = score_pair_exact<T, 10, TA>(plane, H, W, a, g, i, jj, ps.ain[i] && ps.bin[jj], thre2_exact, score, prio, bad);
             if (bad) atomicOr(&ms.flags, kStSampleIndex);
             if (ok) {
                 const size_t out_base = ((size_t)h.n * L + h.k) * ws.capC;
@@ -348,9 +350,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                     ws.cand_prio[out_base + pos] = prio;
                     ws.cand_score[out_base + pos] = score;
                     ws.cand_ij[out_base + pos] = ij;
-                    const uint32_t b = __float_as_uint((float)prio);
-                    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                    ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                    if (sizeof(TA) == 4) {  // one-word sort key: only an f32 priority fits
+                        const uint32_t b = __float_as_uint((float)prio);
+                        const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                        ws.cand_key[out_base + pos] = ((unsigned long long)ord << 32) | (unsigned long long)(~ij);
+                    }
                 }
             }
         };
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             for (int j = 0; j < nj; j++) {
                 const int s = j % kPersistSlots, e = j % kMetaSlots;
                 // `full` also means the meta slot's list and counters are recycled (the loader closed item j - kMetaSlots)
-                mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);
+                mbar_wait_tuned(&bar_full[s], (j / kPersistSlots) & 1, a.wait_ns);
                 MetaSlot &ms = s_meta[e];
                 const int npairs = ms.hdr.npairs;
                 if (c0 * 32 < npairs) {  // warps without pairs skip the item
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             // =========================== scorers ===========================
             for (int j = 0; j < nj; j++) {
                 const int e = j % kMetaSlots;
-                mbar_wait_sleep(&bar_screened[e], (j / kMetaSlots) & 1);  // every screener has left item j: the list is complete
+                mbar_wait_tuned(&bar_screened[e], (j / kMetaSlots) & 1, a.wait_ns);  // every screener has left item j: the list is complete
                 MetaSlot &ms = s_meta[e];
                 const int ns = SPG_DBG(a.debug == 2) ? 0 : min(ms.nsurv, kPersistListCap);
                 if (ns > 0) {

@@ -1,0 +1,215 @@
+// postnet.cuh -- K0: the post-network stage of predict(), one fused kernel per scale.
+//
+// Replaces the body of the scale loop of predict() after the forward pass, /root/reference/evaluate.py:126-161:
+//   split the two outputs (image, mirrored image) into body-part / keypoint channels        (:128-136)
+//   flip ensemble: mirror the second output back, permute its channels, average            (:139-140)
+//   cv2.resize(..., fx=stride, fy=stride, INTER_CUBIC)                                      (:143, :152)
+//   crop the padding                                                                        (:148, :157)
+//   cv2.resize(..., (image_w, image_h), INTER_CUBIC)                                        (:149, :158)
+//   heatmap_avg += heatmap / n ; paf_avg += paf / n   (float64 accumulators, :160-161; find_peaks casts the
+//   keypoint maps back to float32, :173)
+// so that the maps the grouping kernels read are produced on the device, in the layout they stream
+// (channel-first planes), and never visit the host.
+//
+// Arithmetic: OpenCV's generic bicubic path as restated -- and pinned to cv2 -- by oracle/postnet_port.py
+// (coordinate (d + 0.5) * scale - 0.5 in double rounded to float, A = -0.75 coefficients in float32, taps clamped to
+// the source, a float32 horizontal pass whose result is rounded to float32, then a float32 vertical pass; taps are
+// multiplied and added left to right, one rounding per operation).  This translation unit is built with
+// -fmad=false and the code spells out every *_rn operation, so the kernel's maps are BIT-IDENTICAL to the port's
+// (tests/test_gpu_postnet.py), which in turn is within 2.8e-5 of cv2 (the IPP build in the reference's wheels is not
+// bit-defined across hosts: DESIGN.md §8).
+//
+// One CTA computes one output tile of one channel of one image and runs the four separable passes through shared
+// memory: source tile (flip-averaged while it is loaded) -> horizontal x stride -> vertical x stride (= the cropped
+// intermediate the reference materialises at full size) -> horizontal to the image grid -> vertical to the image
+// grid -> epilogue (scale by 1/n in float32, accumulate in float64, store).  HBM traffic is the network output once
+// (x ~1.2 for tile halos) plus the output planes once; the 48 x Hp x Wp float32 intermediate never exists in memory.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace spg {
+
+constexpr int kPostThreads = 256;
+constexpr int kPostTW = 64, kPostTH = 32;     // largest output tile
+constexpr int kPostC1 = 96, kPostR1 = 48;     // capacity of the intermediate (cropped, x stride) tile (static shared memory <= 48 KB)
+constexpr int kPostCS = 32, kPostRS = 20;     // capacity of the source tile (network resolution)
+constexpr int kMaxNetChannels = 64;
+
+struct PostArgs {
+    const void *net;            // [N][2][C][h][w]: image, mirrored image (evaluate.py:116-126)
+    int net_is_f16;             // 0: float32, 1: float16 (converted on load)
+    long long img_stride, pair_stride, chan_stride;  // elements
+    int h, w;                   // network output size
+    int stride;                 // model_params['stride']
+    int crop_h, crop_w;         // imageToTest size = padded size minus pad[2], pad[3] (pad[0] = pad[1] = 0 always)
+    int H, W;                   // image size = output size
+    int n_out;                  // output channels handled: K keypoint + L body-part
+    int K;                      // first K outputs are keypoint channels
+    short src_chan[kMaxNetChannels];   // network channel of output c (keypoints: heat_chan0 + c; body parts: paf_chan0 + k)
+    short flip_chan[kMaxNetChannels];  // network channel of the mirrored output that is averaged into output c
+    float *heat;                // [N][K][H][W] float32 (what find_peaks reads after its cast, evaluate.py:173)
+    void *paf;                  // [N][L][H][W] float32 (single scale: the float64 values are exact float32) or float64
+    double *heat_acc;           // [N][K][H][W] float64 scratch, only for n_scales > 1
+    int paf_is_f64;
+    int scale_index, n_scales;  // accumulate over the scale loop (:160-161)
+    int nan_scrub;              // demo_image.py:179-180: NaN -> 0 after the accumulation
+    int tile_w, tile_h, tiles_x, tiles_y;
+    double sx1, sy1, sx2, sy2;  // source step per destination pixel of the two resizes
+};
+
+// interpolateCubic (imgproc/src/resize.cpp), float32, exactly oracle/postnet_port.py::cubic_coeffs
+__device__ __forceinline__ void cubic_coeffs(float x, float c[4]) {
+    const float A = -0.75f;
+    const float x1 = __fadd_rn(x, 1.0f);
+    c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), __fmul_rn(5.0f, A)), x1), __fmul_rn(8.0f, A)), x1), __fmul_rn(4.0f, A));
+    const float a2 = __fadd_rn(A, 2.0f), a3 = __fadd_rn(A, 3.0f);
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(a2, x), a3), x), x), 1.0f);
+    const float y = __fsub_rn(1.0f, x);
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(a2, y), a3), y), y), 1.0f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, c[0]), c[1]), c[2]);
+}
+
+// destination index d of an axis -> first tap (s - 1, unclamped) and the four weights
+__device__ __forceinline__ int axis_entry(int d, double scale, float c[4]) {
+    const float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);  // fx = (float)((dx+0.5)*scale_x - 0.5)
+    const float fl = floorf(f);
+    cubic_coeffs(__fsub_rn(f, fl), c);
+    return (int)fl - 1;
+}
+
+__device__ __forceinline__ float tap4(float a0, float a1, float a2, float a3, const float *c) {
+    // taps summed left to right, every product and sum rounded to float32
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c[0]), __fmul_rn(a1, c[1])), __fmul_rn(a2, c[2])), __fmul_rn(a3, c[3]));
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+struct AxisTab {  // per destination index of a tile: first tap (absolute source index, unclamped) + weights
+    int s;
+    float c[4];
+};
+
+__global__ void __launch_bounds__(kPostThreads) postnet_kernel(PostArgs a) {
+    __shared__ AxisTab t2x[kPostTW], t2y[kPostTH], t1x[kPostC1], t1y[kPostR1];
+    __shared__ float s0[kPostRS * kPostCS];     // source tile, flip-averaged
+    __shared__ float s1[kPostRS * kPostC1];     // after the horizontal x stride pass
+    __shared__ float s2[kPostR1 * kPostC1];     // after the vertical x stride pass = the cropped intermediate
+    __shared__ float s3[kPostR1 * kPostTW];     // after the horizontal pass of the second resize
+    __shared__ int r_lo[4];                     // c_lo, r_lo of the intermediate tile; source col / row origin
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, c = blockIdx.y, n = blockIdx.z;
+    const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+    const int ox0 = tx * a.tile_w, oy0 = ty * a.tile_h;
+    const int tw = min(a.tile_w, a.W - ox0), th = min(a.tile_h, a.H - oy0);
+    const bool identity = a.crop_h == a.H && a.crop_w == a.W;  // second resize with scale 1: weights (0, 1, 0, 0)
+
+    // ---- tables of the second resize for this tile's output columns / rows
+    if (tid < tw) t2x[tid].s = axis_entry(ox0 + tid, a.sx2, t2x[tid].c);
+    if (tid >= 64 && tid < 64 + th) t2y[tid - 64].s = axis_entry(oy0 + tid - 64, a.sy2, t2y[tid - 64].c);
+    __syncthreads();
+    if (tid == 0) {
+        // crop-coordinate range the tile reads (taps clamped to the cropped array, :148-149)
+        const int c_lo = identity ? ox0 : clampi(t2x[0].s, 0, a.crop_w - 1), c_hi = identity ? ox0 + tw - 1 : clampi(t2x[tw - 1].s + 3, 0, a.crop_w - 1);
+        const int rr_lo = identity ? oy0 : clampi(t2y[0].s, 0, a.crop_h - 1), rr_hi = identity ? oy0 + th - 1 : clampi(t2y[th - 1].s + 3, 0, a.crop_h - 1);
+        r_lo[0] = c_lo; r_lo[1] = c_hi - c_lo + 1;
+        r_lo[2] = rr_lo; r_lo[3] = rr_hi - rr_lo + 1;
+    }
+    __syncthreads();
+    const int c_lo = r_lo[0], C1 = r_lo[1], y_lo = r_lo[2], R1 = r_lo[3];
+    // ---- tables of the first resize (x stride) for the intermediate columns / rows of the tile
+    if (tid < C1) t1x[tid].s = axis_entry(c_lo + tid, a.sx1, t1x[tid].c);
+    if (tid >= 128 && tid < 128 + R1) t1y[tid - 128].s = axis_entry(y_lo + tid - 128, a.sy1, t1y[tid - 128].c);
+    __syncthreads();
+    const int sc_lo = clampi(t1x[0].s, 0, a.w - 1), sc_hi = clampi(t1x[C1 - 1].s + 3, 0, a.w - 1);
+    const int sr_lo = clampi(t1y[0].s, 0, a.h - 1), sr_hi = clampi(t1y[R1 - 1].s + 3, 0, a.h - 1);
+    const int CS = sc_hi - sc_lo + 1, RS = sr_hi - sr_lo + 1;
+
+    // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
+    {
+        const long long base0 = (long long)n * a.img_stride + (long long)a.src_chan[c] * a.chan_stride;
+        const long long base1 = (long long)n * a.img_stride + a.pair_stride + (long long)a.flip_chan[c] * a.chan_stride;
+        for (int e = tid; e < RS * CS; e += kPostThreads) {
+            const int i = e / CS, j = e - i * CS;
+            const int y = sr_lo + i, x = sc_lo + j;
+            float v0, v1;
+            if (a.net_is_f16) {
+                const __half *p = static_cast<const __half *>(a.net);
+                v0 = __half2float(p[base0 + (long long)y * a.w + x]);
+                v1 = __half2float(p[base1 + (long long)y * a.w + (a.w - 1 - x)]);
+            } else {
+                const float *p = static_cast<const float *>(a.net);
+                v0 = p[base0 + (long long)y * a.w + x];
+                v1 = p[base1 + (long long)y * a.w + (a.w - 1 - x)];
+            }
+            s0[i * kPostCS + j] = __fdiv_rn(__fadd_rn(v0, v1), 2.0f);
+        }
+    }
+    __syncthreads();
+    // ---- pass 1: horizontal x stride on every source row of the tile
+    for (int e = tid; e < RS * C1; e += kPostThreads) {
+        const int i = e / C1, X = e - i * C1;
+        const AxisTab &t = t1x[X];
+        const float *row = s0 + i * kPostCS - sc_lo;
+        s1[i * kPostC1 + X] = tap4(row[clampi(t.s, 0, a.w - 1)], row[clampi(t.s + 1, 0, a.w - 1)], row[clampi(t.s + 2, 0, a.w - 1)],
+                                   row[clampi(t.s + 3, 0, a.w - 1)], t.c);
+    }
+    __syncthreads();
+    // ---- pass 2: vertical x stride -> the cropped intermediate (what the reference holds after :148 / :157)
+    for (int e = tid; e < R1 * C1; e += kPostThreads) {
+        const int Y = e / C1, X = e - Y * C1;
+        const AxisTab &t = t1y[Y];
+        const float *col = s1 + X - sr_lo * kPostC1;
+        s2[Y * kPostC1 + X] = tap4(col[clampi(t.s, 0, a.h - 1) * kPostC1], col[clampi(t.s + 1, 0, a.h - 1) * kPostC1],
+                                   col[clampi(t.s + 2, 0, a.h - 1) * kPostC1], col[clampi(t.s + 3, 0, a.h - 1) * kPostC1], t.c);
+    }
+    __syncthreads();
+    // ---- pass 3: horizontal pass of the second resize (clamped to the cropped array)
+    if (!identity) {
+        for (int e = tid; e < R1 * tw; e += kPostThreads) {
+            const int Y = e / tw, x = e - Y * tw;
+            const AxisTab &t = t2x[x];
+            const float *row = s2 + Y * kPostC1 - c_lo;
+            s3[Y * kPostTW + x] = tap4(row[clampi(t.s, 0, a.crop_w - 1)], row[clampi(t.s + 1, 0, a.crop_w - 1)],
+                                       row[clampi(t.s + 2, 0, a.crop_w - 1)], row[clampi(t.s + 3, 0, a.crop_w - 1)], t.c);
+        }
+        __syncthreads();
+    }
+    // ---- pass 4 + epilogue: vertical pass, / n in float32, float64 accumulation over the scale loop (:160-161)
+    const float nf = (float)a.n_scales;
+    const size_t plane = (size_t)a.H * a.W;
+    const bool is_heat = c < a.K;
+    const size_t pbase = is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane;
+    const bool first = a.scale_index == 0, last = a.scale_index == a.n_scales - 1;
+    for (int e = tid; e < th * tw; e += kPostThreads) {
+        const int y = e / tw, x = e - y * tw;
+        float v;
+        if (identity) {
+            v = s2[y * kPostC1 + x];
+        } else {
+            const AxisTab &t = t2y[y];
+            const float *col = s3 + x - y_lo * kPostTW;
+            v = tap4(col[clampi(t.s, 0, a.crop_h - 1) * kPostTW], col[clampi(t.s + 1, 0, a.crop_h - 1) * kPostTW],
+                     col[clampi(t.s + 2, 0, a.crop_h - 1) * kPostTW], col[clampi(t.s + 3, 0, a.crop_h - 1) * kPostTW], t.c);
+        }
+        const size_t o = pbase + (size_t)(oy0 + y) * a.W + (ox0 + x);
+        const float part = __fdiv_rn(v, nf);  // float32 array / Python int -> float32
+        if (a.n_scales == 1) {  // avg = 0.0 + part: exact, the float64 value is the float32 one
+            const float r = (a.nan_scrub && part != part) ? 0.0f : part;
+            if (is_heat) a.heat[o] = r;
+            else if (a.paf_is_f64) static_cast<double *>(a.paf)[o] = (double)r;
+            else static_cast<float *>(a.paf)[o] = r;
+        } else {
+            double *acc = is_heat ? a.heat_acc : static_cast<double *>(a.paf);
+            double s = __dadd_rn(first ? 0.0 : acc[o], (double)part);
+            if (a.nan_scrub && s != s) s = 0.0;  // demo_image.py:179-180 scrubs after every scale
+            acc[o] = s;
+            if (is_heat && last) a.heat[o] = (float)s;  // find_peaks: heatmap_avg.astype(np.float32)
+        }
+    }
+}
+
+}  // namespace spg

@@ -22,8 +22,10 @@
 #include "limb_match.cuh"
 #include "limb_score.cuh"
 #include "limb_score_persist.cuh"
+#include "match_assemble.cuh"
 #include "nms_peaks.cuh"
 #include "nms_peaks_persist.cuh"
+#include "postnet.cuh"
 
 using namespace spg;
 
@@ -41,6 +43,8 @@ struct spg_handle {
     // staging for spg_group_host
     void *in_heat = nullptr, *in_paf = nullptr;
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
+    double *heat_acc = nullptr;  // postnet: float64 accumulator of the keypoint maps over the scale loop
+    size_t heat_acc_elems = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
     const char *stage_kernel[4] = {"", "", "", ""};
@@ -48,6 +52,8 @@ struct spg_handle {
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
     int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
+    int wait_ns = 0;      // persistent kernels: explicit back-off between mbarrier polls (SPG_WAIT_NS; 0 = suspend-hint wait)
+    int fuse_ma = 1;      // whole-path calls run the fused match+assemble kernel (SPG_FUSE_MA=0: the two kernels back to back)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
     std::string err;
@@ -125,6 +131,7 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
     a.image_base = base;
     a.thr = (float)p->thre1;
+    a.wait_ns = h->wait_ns;
     a.ws = h->ws;
     if (h->persist && a.use_bulk && nms_persist_smem_bytes(H, W, h->ws.capP) <= h->smem_optin && (size_t)H * W / 4 < 65536 &&
         (size_t)H * W * sizeof(float) < (1u << 20) &&
@@ -149,7 +156,7 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     return SPG_OK;
 }
 
-template <typename T>
+template <typename T, typename TA = T>
 int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
     const size_t plane_bytes = (size_t)a.H * a.W * sizeof(T);
     const size_t staged = score_smem_bytes(plane_bytes, h->ws.capP);
@@ -160,17 +167,17 @@ int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
         persist_smem_bytes(plane_bytes, h->ws.capP) <= h->smem_optin) {
         // one resident CTA per SM walking a ring of 3 plane slots (loader / screeners / scorers)
         const size_t smem = persist_smem_bytes(plane_bytes, h->ws.capP);
-        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        limb_score_persist_kernel<<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
-        h->stage_kernel[1] = "limb_score_persist_kernel";
+        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limb_score_persist_kernel<TA><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+        h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float>" : "limb_score_persist_kernel<double>";
     } else if (aligned && staged <= h->smem_optin) {
-        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
-        limb_score_kernel<T, true><<<grid, kScoreThreads, staged, st>>>(a);
-        h->stage_kernel[1] = sizeof(T) == 4 ? "limb_score_kernel<float,true>" : "limb_score_kernel<double,true>";
+        SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_kernel<T, true, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged)));
+        limb_score_kernel<T, true, TA><<<grid, kScoreThreads, staged, st>>>(a);
+        h->stage_kernel[1] = sizeof(T) == 8 ? "limb_score_kernel<double,true>" : sizeof(TA) == 4 ? "limb_score_kernel<float,true>" : "limb_score_kernel<float,true,double>";
     } else {  // plane larger than shared memory (or unaligned): sample through L2
         const size_t smem = score_smem_bytes(0, h->ws.capP);
-        limb_score_kernel<T, false><<<grid, kScoreThreads, smem, st>>>(a);
-        h->stage_kernel[1] = sizeof(T) == 4 ? "limb_score_kernel<float,false>" : "limb_score_kernel<double,false>";
+        limb_score_kernel<T, false, TA><<<grid, kScoreThreads, smem, st>>>(a);
+        h->stage_kernel[1] = sizeof(T) == 8 ? "limb_score_kernel<double,false>" : sizeof(TA) == 4 ? "limb_score_kernel<float,false>" : "limb_score_kernel<float,false,double>";
     }
     h->launches++;
     SPG_CUDA(h, cudaGetLastError());
@@ -198,9 +205,12 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     if (const char *e = getenv("SPG_DEBUG_PERSIST")) a.debug = atoi(e);
 #endif
     a.exact_warps = h->exact_warps;
+    a.wait_ns = h->wait_ns;
     a.ws = h->ws;
     h->cand_dtype = dtype;
-    return dtype == SPG_F64 ? launch_score_t<double>(h, a, n, st) : launch_score_t<float>(h, a, n, st);
+    if (dtype == SPG_F64) return launch_score_t<double>(h, a, n, st);
+    if (dtype == SPG_F32_AS_F64) return launch_score_t<float, double>(h, a, n, st);
+    return launch_score_t<float>(h, a, n, st);
 }
 
 int launch_match(spg_handle *h, int base, int n, cudaStream_t st) {
@@ -243,12 +253,38 @@ int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStr
     return SPG_OK;
 }
 
+int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStream_t st) {
+    if (n == 0) return SPG_OK;
+    AssembleArgs a{};
+    a.n_images = n;
+    a.image_base = base;
+    a.len_rate = p->len_rate;
+    a.connection_tole = p->connection_tole;
+    a.min_mean_score = p->min_mean_score;
+    a.remove_recon = p->remove_recon;
+    a.min_parts = p->min_parts;
+    a.refresh_len_check = p->refresh_len_check != 0;
+    a.ws = h->ws;
+    a.ws.wire_first += base;
+    a.use_bulk = 0;
+    const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR) + assemble_conn_bytes(h->ws.L, h->ws.capP);
+    if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "capacities need %zu B of shared memory in match_assemble (limit %zu)", smem, h->smem_optin);
+    SPG_CUDA(h, cudaFuncSetAttribute(match_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_assemble_kernel<<<n, kMAThreads, smem, st>>>(a, h->cand_dtype == SPG_F32);
+    h->stage_kernel[2] = "match_assemble_kernel";
+    h->stage_kernel[3] = "";
+    h->launches++;
+    SPG_CUDA(h, cudaGetLastError());
+    return SPG_OK;
+}
+
 int run_all(spg_handle *h, const float *heat, int64_t his, int64_t hcs, const void *paf, int dtype, int64_t pis, int64_t pcs,
             int base, int n, int H, int W, double extent, const spg_params *p, cudaStream_t st) {
     int rc;
     SPG_CUDA(h, cudaMemsetAsync(h->ws.status + base, 0, sizeof(uint32_t) * (size_t)n, st));
     if ((rc = launch_nms(h, heat, his, hcs, base, n, H, W, p, st))) return rc;
     if ((rc = launch_score(h, paf, dtype, pis, pcs, base, n, H, W, extent, p, st))) return rc;
+    if (h->fuse_ma) return launch_match_assemble(h, base, n, p, st);
     if ((rc = launch_match(h, base, n, st))) return rc;
     if ((rc = launch_assemble(h, base, n, p, st))) return rc;
     return SPG_OK;
@@ -311,6 +347,8 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
+    if (const char *e = getenv("SPG_WAIT_NS")) h->wait_ns = std::max(0, std::min(100000, atoi(e)));
+    if (const char *e = getenv("SPG_FUSE_MA")) h->fuse_ma = !(e[0] == '0');
     if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener
     DeviceGuard guard(h->device);
 
@@ -362,6 +400,7 @@ void spg_destroy(spg_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->in_heat) cudaFree(h->in_heat);
     if (h->in_paf) cudaFree(h->in_paf);
+    if (h->heat_acc) cudaFree(h->heat_acc);
     for (auto &s : h->streams)
         if (s) cudaStreamDestroy(s);
     delete h;
@@ -482,6 +521,77 @@ int64_t spg_launch_count(const spg_handle *h) { return h ? h->launches : 0; }
 
 const char *spg_stage_kernel(const spg_handle *h, int32_t stage) { return (h && stage >= 0 && stage < 4) ? h->stage_kernel[stage] : ""; }
 
+// ---- post-network stage ------------------------------------------------------------------------
+int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, int32_t W, float *heat_out, void *paf_out,
+                int32_t paf_dtype, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (!d || !d->scales || d->n_scales < 1 || !d->flip_paf_ord || !d->flip_heat_ord) return fail(h, SPG_E_INVALID, "postnet descriptor incomplete");
+    if ((!heat_out || !paf_out) && n > 0) return fail(h, SPG_E_INVALID, "heat_out/paf_out is NULL");
+    if (paf_dtype != SPG_F32 && paf_dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    if (paf_dtype == SPG_F32 && d->n_scales != 1)
+        return fail(h, SPG_E_INVALID, "float32 body-part planes hold the reference's float64 values only for a single scale");
+    if (d->stride < 1 || d->stride > 16) return fail(h, SPG_E_INVALID, "stride outside [1,16]");
+    int rc;
+    if ((rc = check_dims(h, n, H, W))) return rc;
+    if (n == 0) return SPG_OK;
+    const Workspace &ws = h->ws;
+    if (ws.K + ws.L > kMaxNetChannels) return fail(h, SPG_E_INVALID, "too many channels for postnet");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->n_scales > 1) {
+        const size_t need = (size_t)h->cfg.max_batch * ws.K * H * W;
+        if (h->heat_acc_elems < need) {
+            if (h->heat_acc) cudaFree(h->heat_acc);
+            h->heat_acc = nullptr; h->heat_acc_elems = 0;
+            SPG_CUDA(h, cudaMalloc(&h->heat_acc, need * sizeof(double)));
+            h->heat_acc_elems = need;
+        }
+    }
+    for (int t = 0; t < d->n_scales; t++) {
+        const spg_postnet_scale &sc = d->scales[t];
+        if (!sc.net_out) return fail(h, SPG_E_INVALID, "scale %d: net_out is NULL", t);
+        if (sc.dtype != SPG_F32 && sc.dtype != SPG_F16) return fail(h, SPG_E_INVALID, "scale %d: network output must be SPG_F32 or SPG_F16", t);
+        if (sc.h < 1 || sc.w < 1 || sc.crop_h < 1 || sc.crop_w < 1 || sc.crop_h > sc.h * d->stride || sc.crop_w > sc.w * d->stride)
+            return fail(h, SPG_E_INVALID, "scale %d: crop %dx%d does not fit the up-sampled %dx%d output", t, sc.crop_h, sc.crop_w, sc.h * d->stride, sc.w * d->stride);
+        PostArgs a{};
+        a.net = sc.net_out; a.net_is_f16 = sc.dtype == SPG_F16;
+        a.img_stride = sc.image_stride; a.pair_stride = sc.pair_stride; a.chan_stride = sc.chan_stride;
+        a.h = sc.h; a.w = sc.w; a.stride = d->stride; a.crop_h = sc.crop_h; a.crop_w = sc.crop_w;
+        a.H = H; a.W = W; a.n_out = ws.K + ws.L; a.K = ws.K;
+        for (int c = 0; c < ws.K; c++) {
+            if (d->flip_heat_ord[c] < 0 || d->flip_heat_ord[c] >= ws.K) return fail(h, SPG_E_INVALID, "flip_heat_ord[%d] out of range", c);
+            a.src_chan[c] = (short)(d->heat_chan0 + c);
+            a.flip_chan[c] = (short)(d->heat_chan0 + d->flip_heat_ord[c]);
+        }
+        for (int k = 0; k < ws.L; k++) {
+            if (d->flip_paf_ord[k] < 0 || d->flip_paf_ord[k] >= ws.L) return fail(h, SPG_E_INVALID, "flip_paf_ord[%d] out of range", k);
+            a.src_chan[ws.K + k] = (short)(d->paf_chan0 + k);
+            a.flip_chan[ws.K + k] = (short)(d->paf_chan0 + d->flip_paf_ord[k]);
+        }
+        a.heat = heat_out; a.paf = paf_out; a.heat_acc = h->heat_acc; a.paf_is_f64 = paf_dtype == SPG_F64;
+        a.scale_index = t; a.n_scales = d->n_scales; a.nan_scrub = d->nan_scrub != 0;
+        // cv2.resize(fx = stride): scale = 1/fx;  cv2.resize(dsize): inv_scale = dst/src, scale = 1/inv_scale (two roundings, as OpenCV)
+        a.sx1 = 1.0 / (double)d->stride; a.sy1 = a.sx1;
+        a.sx2 = 1.0 / ((double)W / (double)sc.crop_w);
+        a.sy2 = 1.0 / ((double)H / (double)sc.crop_h);
+        // output tile: as large as the shared-memory tiles of the intermediate / source allow
+        auto tile_dim = [&](double s2, double s1, int cap1, int cap0, int maxd) {
+            const double c1 = std::min((double)cap1, ((double)cap0 - 7.0) / s1) - 7.0;  // intermediate span allowed
+            return std::max(1, std::min(maxd, (int)(c1 / std::max(s2, 1e-6))));
+        };
+        a.tile_w = tile_dim(a.sx2, a.sx1, kPostC1, kPostCS, kPostTW);
+        a.tile_h = tile_dim(a.sy2, a.sy1, kPostR1, kPostRS, kPostTH);
+        a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
+        a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
+        if ((long long)a.tiles_x * a.tiles_y > 0x7fffffffLL || n > 65535) return fail(h, SPG_E_INVALID, "postnet grid too large");
+        dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)a.n_out, (unsigned)n);
+        postnet_kernel<<<grid, kPostThreads, 0, st>>>(a);
+        h->launches++;
+        SPG_CUDA(h, cudaGetLastError());
+    }
+    return SPG_OK;
+}
+
 // ---- stages ------------------------------------------------------------------------------------
 int spg_nms_peaks(spg_handle *h, const float *heat, int64_t image_stride, int64_t chan_stride, int32_t n, int32_t H, int32_t W,
                   const spg_params *p, void *stream) {
@@ -501,7 +611,7 @@ int spg_limb_score(spg_handle *h, const void *paf, int32_t dtype, int64_t image_
                    int32_t W, double extent, const spg_params *p, void *stream) {
     if (!h) return SPG_E_INVALID;
     if (!paf && n > 0) return fail(h, SPG_E_INVALID, "paf_dev is NULL");
-    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    if (dtype != SPG_F32 && dtype != SPG_F64 && dtype != SPG_F32_AS_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32, SPG_F64 or SPG_F32_AS_F64");
     if (h->stage < 1) return fail(h, SPG_E_STATE, "spg_limb_score needs peaks (spg_nms_peaks or spg_upload_peaks) first");
     int rc;
     if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
@@ -535,11 +645,23 @@ int spg_assemble(spg_handle *h, int32_t n, const spg_params *p, void *stream) {
     return SPG_OK;
 }
 
+int spg_match_assemble(spg_handle *h, int32_t n, const spg_params *p, void *stream) {
+    if (!h) return SPG_E_INVALID;
+    if (h->stage < 2) return fail(h, SPG_E_STATE, "spg_match_assemble needs spg_limb_score first");
+    int rc;
+    if (n < 0 || n > h->cfg.max_batch) return fail(h, SPG_E_INVALID, "n_images out of range");
+    if ((rc = check_params(h, p))) return rc;
+    DeviceGuard guard(h->device);
+    if ((rc = launch_match_assemble(h, 0, n, p, static_cast<cudaStream_t>(stream)))) return rc;
+    h->stage = 4;
+    return SPG_OK;
+}
+
 int spg_group_batch(spg_handle *h, const float *heat, int64_t his, int64_t hcs, const void *paf, int32_t dtype, int64_t pis, int64_t pcs,
                     int32_t n, int32_t H, int32_t W, double extent, const spg_params *p, void *stream) {
     if (!h) return SPG_E_INVALID;
     if ((!heat || !paf) && n > 0) return fail(h, SPG_E_INVALID, "heat_dev/paf_dev is NULL");
-    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    if (dtype != SPG_F32 && dtype != SPG_F64 && dtype != SPG_F32_AS_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32, SPG_F64 or SPG_F32_AS_F64");
     int rc;
     if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
     DeviceGuard guard(h->device);
@@ -558,7 +680,7 @@ int spg_group_host(spg_handle *h, const float *heat_host, const void *paf_host, 
                    double extent, const spg_params *p, int32_t *out_n, double *out_xy, double *out_score, uint32_t *out_status) {
     if (!h) return SPG_E_INVALID;
     if ((!heat_host || !paf_host) && n > 0) return fail(h, SPG_E_INVALID, "heat_host/paf_host is NULL");
-    if (dtype != SPG_F32 && dtype != SPG_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32 or SPG_F64");
+    if (dtype != SPG_F32 && dtype != SPG_F64 && dtype != SPG_F32_AS_F64) return fail(h, SPG_E_INVALID, "paf_dtype must be SPG_F32, SPG_F64 or SPG_F32_AS_F64");
     int rc;
     if ((rc = check_dims(h, n, H, W)) || (rc = check_params(h, p))) return rc;
     DeviceGuard guard(h->device);

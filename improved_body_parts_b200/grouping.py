@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libspgroup.so")
 ABI_VERSION = 2
 
 ST_PEAK_OVERFLOW, ST_CAND_OVERFLOW, ST_ROW_OVERFLOW, ST_SAMPLE_INDEX, ST_ASSERT, ST_WIRE_OVERFLOW = 1, 2, 4, 8, 16, 32
-F32, F64 = 0, 1
+F32, F64, F32_AS_F64, F16 = 0, 1, 2, 3
 
 #: every symbol include/spgroup.h declares (checked by tests/test_abi.py against the built library)
 EXPORTS = (
@@ -30,7 +30,7 @@ EXPORTS = (
     "spg_assemble", "spg_upload_peaks", "spg_upload_connections", "spg_download_peaks", "spg_download_connections",
     "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel", "spg_wire_record_bytes",
     "spg_set_wire_output", "spg_wire_create", "spg_wire_open", "spg_wire_close", "spg_wire_destroy", "spg_wire_signal",
-    "spg_wire_wait")
+    "spg_wire_wait", "spg_postnet", "spg_match_assemble")
 
 
 class GroupingError(RuntimeError):
@@ -49,6 +49,17 @@ class _Params(C.Structure):
                 ("len_rate", C.c_double), ("connection_tole", C.c_double), ("min_mean_score", C.c_double),
                 ("mid_num", C.c_int32), ("offset_radius", C.c_int32), ("remove_recon", C.c_int32),
                 ("min_parts", C.c_int32), ("crit1_strict", C.c_int32), ("refresh_len_check", C.c_int32)]
+
+
+class _PostnetScale(C.Structure):
+    _fields_ = [("net_out", C.c_void_p), ("dtype", C.c_int32), ("image_stride", C.c_int64), ("pair_stride", C.c_int64),
+                ("chan_stride", C.c_int64), ("h", C.c_int32), ("w", C.c_int32), ("crop_h", C.c_int32), ("crop_w", C.c_int32)]
+
+
+class _PostnetDesc(C.Structure):
+    _fields_ = [("n_scales", C.c_int32), ("scales", C.POINTER(_PostnetScale)), ("stride", C.c_int32),
+                ("paf_chan0", C.c_int32), ("heat_chan0", C.c_int32), ("flip_paf_ord", C.POINTER(C.c_int32)),
+                ("flip_heat_ord", C.POINTER(C.c_int32)), ("nan_scrub", C.c_int32)]
 
 
 class _DeviceView(C.Structure):
@@ -329,16 +340,16 @@ class Grouper:
             raise GroupingError(f"{name} must be [N,C,H,W] with contiguous rows (pixel stride 1, row stride W)")
         return t
 
-    def _paf_dtype(self, paf) -> int:
+    def _paf_dtype(self, paf, as_f64: bool = False) -> int:
         import torch
         if paf.dtype == torch.float32:
-            return F32
+            return F32_AS_F64 if as_f64 else F32
         if paf.dtype == torch.float64:
             return F64
         raise GroupingError("body-part maps must be float32 or float64")
 
     # -- whole path --------------------------------------------------------------------------------
-    def group_device(self, heat, paf, image_extent: float, params=None, stream=None) -> None:
+    def group_device(self, heat, paf, image_extent: float, params=None, stream=None, paf_as_f64: bool = False) -> None:
         """peaks -> connections -> people on device-resident maps; asynchronous on ``stream``.
 
         ``heat [N,>=K,H,W] float32`` (first K channels are used) and ``paf [N,>=L,H,W] float32|float64`` CUDA
@@ -354,10 +365,11 @@ class Grouper:
         p = params_struct(params)
         rc = self._lib.spg_group_batch(self._h, C.c_void_p(heat.data_ptr()), C.c_int64(heat.stride(0)),
                                        C.c_int64(heat.stride(1)), C.c_void_p(paf.data_ptr()),
-                                       C.c_int32(self._paf_dtype(paf)), C.c_int64(paf.stride(0)), C.c_int64(paf.stride(1)),
+                                       C.c_int32(self._paf_dtype(paf, paf_as_f64)), C.c_int64(paf.stride(0)), C.c_int64(paf.stride(1)),
                                        C.c_int32(N), C.c_int32(H), C.c_int32(W), C.c_double(float(image_extent)),
                                        C.byref(p), self._stream_ptr(stream))
         self._check(rc, "spg_group_batch")
+        self._peaks_shape = (N, H, W)
         self._last_n = N
 
     def group_host(self, heat: np.ndarray, paf: np.ndarray, image_extent: float, params=None, out=None) -> dict:
@@ -387,6 +399,60 @@ class Grouper:
         self._last_n = N
         return out
 
+    # -- post-network stage ---------------------------------------------------------------------------
+    def postnet(self, net_outs, crops, out_hw, *, stride: int = 4, paf_dtype=None, heat_out=None, paf_out=None,
+                paf_chan0: int = 0, heat_chan0: Optional[int] = None, flip_paf_ord=None, flip_heat_ord=None,
+                nan_scrub: bool = False, stream=None):
+        """The scale loop of ``predict()`` after the forward pass (evaluate.py:126-161) on the device.
+
+        ``net_outs``: one CUDA tensor ``[N, 2, C, h, w]`` (float32 / float16; image, mirrored image) per scale;
+        ``crops``: per scale ``(crop_h, crop_w)`` = ``imageToTest.shape[:2]``; ``out_hw``: the image size.
+        Returns ``(heat [N,K,H,W] float32, paf [N,L,H,W])`` -- ``paf`` float32 for a single scale (pass
+        ``paf_as_f64=True`` to the grouping calls: the reference's float64 values are exactly these), float64 otherwise.
+        """
+        import torch
+        from .skeleton import FLIP_HEAT_ORD, FLIP_PAF_ORD, NUM_LIMBS
+        if len(net_outs) != len(crops) or not net_outs:
+            raise GroupingError("one crop size per scale expected")
+        H, W = (int(v) for v in out_hw)
+        N = int(net_outs[0].shape[0])
+        dev = torch.device("cuda", self.device)
+        single = len(net_outs) == 1
+        if paf_dtype is None:
+            paf_dtype = torch.float32 if single else torch.float64
+        if paf_dtype == torch.float32 and not single:
+            raise GroupingError("float32 body-part planes hold the reference's float64 values only for a single scale")
+        heat_chan0 = self.L if heat_chan0 is None else heat_chan0
+        fp = np.ascontiguousarray(np.asarray(FLIP_PAF_ORD if flip_paf_ord is None else flip_paf_ord, np.int32)[:self.L])
+        fh = np.ascontiguousarray(np.asarray(FLIP_HEAT_ORD if flip_heat_ord is None else flip_heat_ord, np.int32)[:self.K])
+        if flip_paf_ord is None and self.L != NUM_LIMBS:
+            raise GroupingError("flip_paf_ord is needed for a non-canonical skeleton")
+        scales = (_PostnetScale * len(net_outs))()
+        for t, (o, (ch, cw)) in enumerate(zip(net_outs, crops)):
+            if not o.is_cuda or o.device.index != self.device or o.dim() != 5 or o.shape[0] != N or o.shape[1] != 2:
+                raise GroupingError("network output must be a [N,2,C,h,w] CUDA tensor on the handle's device")
+            if o.stride(4) != 1 or o.stride(3) != o.shape[4]:
+                raise GroupingError("network output rows must be contiguous")
+            if o.dtype not in (torch.float32, torch.float16):
+                raise GroupingError("network output must be float32 or float16")
+            if o.shape[2] < max(heat_chan0 + self.K, paf_chan0 + self.L):
+                raise GroupingError("network output has too few channels")
+            scales[t] = _PostnetScale(o.data_ptr(), F32 if o.dtype == torch.float32 else F16, o.stride(0), o.stride(1),
+                                      o.stride(2), o.shape[3], o.shape[4], int(ch), int(cw))
+        if heat_out is None:
+            heat_out = torch.empty((N, self.K, H, W), dtype=torch.float32, device=dev)
+        if paf_out is None:
+            paf_out = torch.empty((N, self.L, H, W), dtype=paf_dtype, device=dev)
+        if not (heat_out.is_contiguous() and paf_out.is_contiguous()) or paf_out.dtype != paf_dtype:
+            raise GroupingError("heat_out / paf_out must be contiguous tensors of the requested dtype")
+        desc = _PostnetDesc(len(net_outs), scales, int(stride), int(paf_chan0), int(heat_chan0),
+                            fp.ctypes.data_as(C.POINTER(C.c_int32)), fh.ctypes.data_as(C.POINTER(C.c_int32)), int(bool(nan_scrub)))
+        rc = self._lib.spg_postnet(self._h, C.byref(desc), C.c_int32(N), C.c_int32(H), C.c_int32(W),
+                                   C.c_void_p(heat_out.data_ptr()), C.c_void_p(paf_out.data_ptr()),
+                                   C.c_int32(F32 if paf_dtype == torch.float32 else F64), self._stream_ptr(stream))
+        self._check(rc, "spg_postnet")
+        return heat_out, paf_out
+
     # -- stages -------------------------------------------------------------------------------------
     def nms_peaks(self, heat, params=None, stream=None) -> None:
         """find_peaks (evaluate.py:169-203) on ``heat [N,>=K,H,W]`` float32 CUDA."""
@@ -401,7 +467,7 @@ class Grouper:
         self._check(rc, "spg_nms_peaks")
         self._last_n = N
 
-    def limb_score(self, paf, image_extent: float, params=None, stream=None) -> None:
+    def limb_score(self, paf, image_extent: float, params=None, stream=None, paf_as_f64: bool = False) -> None:
         """Scoring half of find_connections (evaluate.py:211-255) for peaks already on the device."""
         import torch
         self._check_maps(paf, "paf", self.L, (torch.float32, torch.float64))
@@ -410,7 +476,7 @@ class Grouper:
         if ps is not None and (ps[0] < N or ps[1:] != (H, W)):
             raise GroupingError(f"paf is {N}x{H}x{W} but the peaks on the device come from {ps[0]}x{ps[1]}x{ps[2]} heat maps")
         p = params_struct(params)
-        rc = self._lib.spg_limb_score(self._h, C.c_void_p(paf.data_ptr()), C.c_int32(self._paf_dtype(paf)),
+        rc = self._lib.spg_limb_score(self._h, C.c_void_p(paf.data_ptr()), C.c_int32(self._paf_dtype(paf, paf_as_f64)),
                                       C.c_int64(paf.stride(0)), C.c_int64(paf.stride(1)), C.c_int32(N), C.c_int32(H),
                                       C.c_int32(W), C.c_double(float(image_extent)), C.byref(p), self._stream_ptr(stream))
         self._check(rc, "spg_limb_score")
@@ -427,6 +493,12 @@ class Grouper:
         p = params_struct(params)
         self._check(self._lib.spg_assemble(self._h, C.c_int32(n_images), C.byref(p), self._stream_ptr(stream)),
                     "spg_assemble")
+
+    def match_assemble(self, n_images: int, params=None, stream=None) -> None:
+        """limb_match + assemble fused in one kernel (what the whole-path calls run)."""
+        p = params_struct(params)
+        self._check(self._lib.spg_match_assemble(self._h, C.c_int32(n_images), C.byref(p), self._stream_ptr(stream)),
+                    "spg_match_assemble")
 
     # -- state transfer ---------------------------------------------------------------------------------
     def upload_peaks(self, image_index: int, part_count, x, y, score, stream=None) -> None:

@@ -50,7 +50,11 @@ enum {
     SPG_ST_WIRE_OVERFLOW = 1u << 5   /* more persons than the wire record holds (rows beyond are dropped) */
 };
 
-enum { SPG_F32 = 0, SPG_F64 = 1 }; /* dtype of the body-part planes (evaluate.py:86 makes them f64) */
+/* dtype of the body-part planes.  predict() accumulates them in float64 (evaluate.py:86,161); with a single scale
+ * (the reference's default, utils/config:26) every float64 value is exactly a float32 one, so the planes can be STORED
+ * as float32 and evaluated with the float64 arithmetic the reference applies: SPG_F32_AS_F64 -- half the HBM traffic,
+ * bit-identical results to SPG_F64 planes holding the same values.  SPG_F16 is accepted for network outputs only. */
+enum { SPG_F32 = 0, SPG_F64 = 1, SPG_F32_AS_F64 = 2, SPG_F16 = 3 };
 
 typedef struct spg_handle spg_handle;
 
@@ -131,6 +135,33 @@ int spg_group_host(spg_handle *h, const float *heat_host, const void *paf_host, 
 int spg_host_alloc(void **ptr, uint64_t bytes);
 int spg_host_free(void *ptr);
 
+/* ---- post-network stage: the scale loop of predict() after the forward pass, evaluate.py:126-161 ----------- */
+/* One entry per (scale) of params['scale_search']: the network's output for a batch of image pairs
+ * [N][2][C][h][w] (image, mirrored image; evaluate.py:116-126), device memory, float32 or float16. */
+typedef struct spg_postnet_scale {
+    const void *net_out;
+    int32_t dtype;                  /* SPG_F32 | SPG_F16 */
+    int64_t image_stride, pair_stride, chan_stride; /* elements; rows are contiguous (row stride w) */
+    int32_t h, w;                   /* network output size = padded input size / stride */
+    int32_t crop_h, crop_w;         /* imageToTest size: padded size minus pad[2] / pad[3] (evaluate.py:148) */
+} spg_postnet_scale;
+typedef struct spg_postnet_desc {
+    int32_t n_scales;               /* len(multiplier) * len(rotate_angle); rotation is not supported (angle == 0) */
+    const spg_postnet_scale *scales;
+    int32_t stride;                 /* model_params['stride'] (4) */
+    int32_t paf_chan0, heat_chan0;  /* first body-part / keypoint channel of the network output (0 / 30, config.py:101-103) */
+    const int32_t *flip_paf_ord;    /* [n_limbs]  config.py:121-124 */
+    const int32_t *flip_heat_ord;   /* [n_parts] */
+    int32_t nan_scrub;              /* demo_image.py:179-180: NaN -> 0 in the averaged maps (evaluate.py: 0) */
+} spg_postnet_desc;
+/* flip ensemble (:139-140) + cv2.resize x stride (:143,152) + crop (:148,157) + cv2.resize to the image (:149,158) +
+ * float64 average over the scales (:160-161), fused, writing the channel-first planes the grouping kernels stream:
+ *   heat_out [N][n_parts][H][W] float32 (the cast of evaluate.py:173 applied),
+ *   paf_out  [N][n_limbs][H][W] SPG_F64, or SPG_F32 when n_scales == 1 (then pass SPG_F32_AS_F64 to the grouping calls).
+ * Interpolation follows OpenCV's generic bicubic path (A = -0.75) operation for operation in float32. */
+int spg_postnet(spg_handle *h, const spg_postnet_desc *desc, int32_t n_images, int32_t height, int32_t width,
+                float *heat_out, void *paf_out, int32_t paf_dtype, void *stream);
+
 /* ---- stage entry points (stage-wise parity; each consumes the previous stage's device state) ---- */
 /* find_peaks: evaluate.py:169-203 = util.keypoint_heatmap_nms (utils/util.py:177-183) + util.refine_centroid (:186-211) */
 int spg_nms_peaks(spg_handle *h, const float *heat_dev, int64_t image_stride, int64_t chan_stride,
@@ -143,6 +174,9 @@ int spg_limb_score(spg_handle *h, const void *paf_dev, int32_t paf_dtype, int64_
 int spg_limb_match(spg_handle *h, int32_t n_images, const spg_params *params, void *stream);
 /* find_people + process() tail: evaluate.py:279-498 and :523-543 */
 int spg_assemble(spg_handle *h, int32_t n_images, const spg_params *params, void *stream);
+/* the two previous stages fused in one kernel (one CTA per image: matcher warps feed the assembler warp limb by limb
+ * through shared memory); what spg_group_batch / spg_group_host run.  Same outputs as the two calls back to back. */
+int spg_match_assemble(spg_handle *h, int32_t n_images, const spg_params *params, void *stream);
 
 /* ---- host <-> device state transfer for the stage-wise drop-in functions ---------------------- */
 /* peaks of ONE image, part-major flat arrays as the reference's all_peaks flattens (evaluate.py:283):
