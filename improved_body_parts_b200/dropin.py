@@ -82,7 +82,66 @@ def _maps_to_device(hwc: np.ndarray, channels: int, dtype):
     return torch.from_numpy(arr).to(f"cuda:{_device}")[None]
 
 
+class DeviceMaps:
+    """Averaged maps that stay on the GPU between ``predict`` and the grouping functions (what ``dropin.predict``
+    returns in place of the reference's ``[H, W, C]`` float64 host arrays).  ``numpy()`` gives the reference's array."""
+
+    def __init__(self, tensor, as_f64: bool):
+        self.tensor, self.as_f64 = tensor, as_f64  # [1, C, H, W]; as_f64: float32 storage of the float64 values
+        self.shape = (int(tensor.shape[2]), int(tensor.shape[3]), int(tensor.shape[1]))
+
+    def numpy(self) -> np.ndarray:
+        return self.tensor[0].permute(1, 2, 0).double().cpu().numpy()
+
+
+#: what the last stage left on the device, so that the next stage does not upload it again when it is handed the very
+#: objects the previous stage returned (the call sequence of evaluate.py:509-511)
+_state: Dict[str, object] = {}
+
+
+def pad_right_down_corner(img: np.ndarray, stride: int, pad_value: int) -> Tuple[np.ndarray, list]:
+    """utils/util.py:44-64: pad below / to the right up to a multiple of ``stride`` with ``pad_value``."""
+    h, w = img.shape[:2]
+    pad = [0, 0, 0 if h % stride == 0 else stride - h % stride, 0 if w % stride == 0 else stride - w % stride]
+    return np.pad(img, ((0, pad[2]), (0, pad[3]), (0, 0)), constant_values=pad_value), pad
+
+
+def predict(image, params, model, model_params, heat_layers=None, paf_layers=None, input_image_path=None):
+    """evaluate.py:83-166 with everything after the forward pass on the device.
+
+    Same arguments as the reference's ``predict``.  The image is scaled and padded exactly as there (cv2, host), the
+    network runs on the image and its mirror (:116-124), and the flip ensemble, both bicubic resizes, the crop and the
+    float64 average over ``scale_search`` (:126-161) happen in ``spg_postnet`` -- the maps never visit the host.
+    Returns two ``DeviceMaps`` (heatmap, paf) that ``find_peaks`` / ``find_connections`` / ``group`` accept directly.
+    ``rotation_search`` other than ``[0]`` (the reference's default, utils/config:27) is not supported."""
+    import cv2
+    import torch
+    if any(float(a) != 0.0 for a in params["rotation_search"]):
+        raise GroupingError("rotation_search other than 0 is not supported by the device post-network stage")
+    g = _grouper()
+    multiplier = [x * model_params["boxsize"] / image.shape[0] for x in params["scale_search"]]
+    outs, crops = [], []
+    for scale in multiplier:
+        if scale * image.shape[0] > 2600 or scale * image.shape[1] > 3800:  # evaluate.py:94-96
+            scale = min(2600 / image.shape[0], 3800 / image.shape[1])
+        image_to_test = cv2.resize(image, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+        padded, _ = pad_right_down_corner(image_to_test, model_params["max_downsample"], model_params["padValue"])
+        input_img = np.float32(padded / 255)
+        pair = np.concatenate((input_img[None, ...], input_img[:, ::-1, :].copy()[None, ...]), axis=0)
+        with torch.no_grad():
+            out = model(torch.from_numpy(pair).to(f"cuda:{_device}"))[-1][0]  # last stack, finest scale (:126)
+        if out.dtype not in (torch.float32, torch.float16):
+            out = out.float()
+        outs.append(out[None].contiguous())
+        crops.append(image_to_test.shape[:2])
+    heat, paf = g.postnet(outs, crops, image.shape[:2], stride=int(model_params["stride"]), nan_scrub=_variant == "demo")
+    return DeviceMaps(heat, False), DeviceMaps(paf, paf.dtype == torch.float32)
+
+
 def _upload_peaks(g: Grouper, all_peaks) -> None:
+    if _state.get("peaks") is all_peaks and _state.get("handle") is g:
+        return  # still on the device from our own find_peaks
+    _state.clear()
     counts = [len(p) for p in all_peaks]
     flat = [t for part in all_peaks for t in part]
     g.upload_peaks(0, counts, [float(t[0]) for t in flat], [float(t[1]) for t in flat], [np.float32(t[2]) for t in flat])
@@ -93,10 +152,14 @@ def find_peaks(heatmap_avg, params):
     """evaluate.py:169-203.  ``heatmap_avg [H,W,>=18]`` -> list[18] of [(x, y, score, id), ...]."""
     H, W = heatmap_avg.shape[:2]
     g = _grouper(H, W)
-    g.nms_peaks(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _params(params))  # the cast is evaluate.py:173
+    heat = heatmap_avg.tensor if isinstance(heatmap_avg, DeviceMaps) else _maps_to_device(heatmap_avg, NUM_PARTS, np.float32)
+    g.nms_peaks(heat, _params(params))  # the cast is evaluate.py:173
     r = g.fetch(1)
     _check(r)
-    return r.as_reference_structures(0)[0]
+    all_peaks = r.as_reference_structures(0)[0]
+    _state.clear()
+    _state.update(peaks=all_peaks, handle=g)
+    return all_peaks
 
 
 def find_connections(all_peaks, paf_avg, image_width, params):
@@ -104,8 +167,11 @@ def find_connections(all_peaks, paf_avg, image_width, params):
     H, W = paf_avg.shape[:2]
     g = _grouper(H, W)
     _upload_peaks(g, all_peaks)
-    dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
-    g.limb_score(_maps_to_device(paf_avg, len(_limbs), dtype), image_width, _params(params))
+    if isinstance(paf_avg, DeviceMaps):
+        g.limb_score(paf_avg.tensor, image_width, _params(params), paf_as_f64=paf_avg.as_f64)
+    else:
+        dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
+        g.limb_score(_maps_to_device(paf_avg, len(_limbs), dtype), image_width, _params(params))
     g.limb_match(1, _params(params))
     r = g.fetch(1)
     _check(r)
@@ -117,12 +183,19 @@ def find_connections(all_peaks, paf_avg, image_width, params):
         a, b = _limbs[k]
         rows[:, 0] = np.array([t[3] for t in all_peaks[a]], np.float64)[rows[:, 3].astype(np.int64)]
         rows[:, 1] = np.array([t[3] for t in all_peaks[b]], np.float64)[rows[:, 4].astype(np.int64)]
+    _state.update(conns=conns, special=special)
     return conns, special
 
 
 def find_people(connection_all, special_k, all_peaks, params):
     """evaluate.py:279-498 -> (subset [P,20,2] float64, candidate [N,4] float64)."""
     g = _grouper()  # assembly does not depend on the map size
+    if _state.get("conns") is connection_all and _state.get("special") is special_k and _state.get("peaks") is all_peaks \
+            and _state.get("handle") is g:  # evaluate.py:509-511 handing our own objects back: everything is still on the device
+        g.assemble(1, _params(params))
+        r = g.fetch(1)
+        _check(r)
+        return r.subset[0, :int(r.n_persons[0])].copy(), np.array([item for sublist in all_peaks for item in sublist])
     _upload_peaks(g, all_peaks)
     special = set(int(k) for k in special_k)
     counts, ij, sc, nm = [], [], [], []
@@ -158,9 +231,13 @@ def group(heatmap_avg, paf_avg, image_extent, params):
     Returns ``(all_peaks, connection_all, special_k, subset, candidate)`` exactly as the three calls would."""
     H, W = heatmap_avg.shape[:2]
     g = _grouper(H, W)
-    dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
-    g.group_device(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _maps_to_device(paf_avg, len(_limbs), dtype),
-                   image_extent, _params(params))
+    _state.clear()
+    if isinstance(heatmap_avg, DeviceMaps):
+        g.group_device(heatmap_avg.tensor, paf_avg.tensor, image_extent, _params(params), paf_as_f64=paf_avg.as_f64)
+    else:
+        dtype = np.float64 if np.asarray(paf_avg).dtype == np.float64 else np.float32
+        g.group_device(_maps_to_device(heatmap_avg, NUM_PARTS, np.float32), _maps_to_device(paf_avg, len(_limbs), dtype),
+                       image_extent, _params(params))
     r = g.fetch(1)
     _check(r)
     return r.as_reference_structures(0)
@@ -191,6 +268,7 @@ def keypoint_heatmap_nms(heat, kernel: int = 3, thre: float = 0.1):
     g = Grouper(((0, 0),), C, (0,), max_batch=1, max_h=MAX_DIM, max_w=MAX_DIM, max_peaks_per_part=CAP_PEAKS,
                 device=_device) if C != NUM_PARTS else _grouper(H, W)
     src = heat.to(f"cuda:{_device}", torch.float32).contiguous()
+    _state.clear()
     g.nms_peaks(src, dict(thre1=float(thre), offset_radius=0))
     r = g.fetch(1)
     _check(r)
@@ -207,11 +285,18 @@ def keypoint_heatmap_nms(heat, kernel: int = 3, thre: float = 0.1):
     return out.to(heat.device)
 
 
-def install(evaluate_module) -> None:
+def install(evaluate_module, device_predict: bool = False) -> None:
     """Rebind ``find_peaks / find_connections / find_people`` of an imported reference ``evaluate`` module.
 
-    ``limbSeq`` is taken from the module (evaluate.py:54) so alternative skeletons keep working."""
+    ``limbSeq`` is taken from the module (evaluate.py:54) so alternative skeletons keep working.  With
+    ``device_predict`` the module's ``predict`` (:83-166) is replaced as well: the network of the module (the global
+    ``posenet`` the reference's own predict uses, :124) feeds the device post-network stage and the maps stay on the GPU."""
     configure(limbs=getattr(evaluate_module, "limbSeq", _limbs))
     evaluate_module.find_peaks = find_peaks
     evaluate_module.find_connections = find_connections
     evaluate_module.find_people = find_people
+    if device_predict:
+        def _predict(image, params, model, model_params, heat_layers, paf_layers, input_image_path):
+            return predict(image, params, getattr(evaluate_module, "posenet", model), model_params, heat_layers,
+                           paf_layers, input_image_path)
+        evaluate_module.predict = _predict
