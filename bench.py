@@ -51,8 +51,13 @@ CONFIGS = {
                 what="BASELINE configs[1]: batch=256 synthetic 128x128x(18+30) f32 maps, 10 persons/img, 1 GPU"),
     "f64": dict(H=128, W=128, persons=30, batch=256, paf="f64", gen={},
                 what="configs[2]'s shard with float64 body-part maps -- the dtype predict() emits (evaluate.py:86,161)"),
-    "512": dict(H=512, W=512, persons=30, batch=32, paf="f32", gen=dict(scale_range=(3.2, 5.2), sigma_scale=4.0),
-                what="BASELINE configs[3]'s map size: batch=32 synthetic 512x512x(18+30) f32 maps (bodies and blobs 4x), 30 persons/img"),
+    # pipeline configurations: the input is the NETWORK OUTPUT; the post-network stage (spg_postnet) is part of every pass
+    "512": dict(H=512, W=512, persons=30, batch=32, paf="f64", gen={}, scales=(0.5, 1.0, 2.0), net_hw=(128, 128),
+                what="BASELINE configs[3]: multi-scale x0.5/1/2 + flip-averaged maps -> grouping, 512x512 image, batch=32: network "
+                     "outputs [32,2,50,{64,128,256}^2] f32 -> spg_postnet -> 512x512x(18 f32 + 30 f64) maps -> grouping, 30 persons/img"),
+    "net128": dict(H=128, W=128, persons=30, batch=256, paf="f32-as-f64", gen={}, scales=(1.0,), net_hw=(32, 32),
+                   what="configs[2]'s shard starting from the network output: [256,2,50,32,32] f32 -> spg_postnet (flip ensemble + x4 "
+                        "bicubic) -> 128x128x(18+30) maps (f32 storage, the reference's f64 arithmetic) -> grouping, 30 persons/img"),
 }
 
 
@@ -69,6 +74,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: packed NCCL gather instead of NVLink peer stores")
+    ap.add_argument("--trace", default="", help="write a per-rank CUDA-event timeline of 8 consecutive passes to this JSON file (rank 0)")
     ap.add_argument("--unfused", action="store_true", help="limb_match and assemble as two kernels instead of the fused match_assemble")
     ap.add_argument("--unmodified", action="store_true",
                     help="--impl reference only, build container only: time the UNMODIFIED reference functions (oracle/ref_loader)")
@@ -77,6 +83,8 @@ def parse_args():
     args.batch = args.batch or cfg["batch"]
     args.persons = args.persons or cfg["persons"]
     args.H, args.W, args.paf = cfg["H"], cfg["W"], cfg["paf"]
+    if args.impl == "reference" and "scales" in cfg:
+        raise SystemExit("the reference arm times the grouping window (evaluate.py:507-513): use --config p30 / p10 / f64")
     return args
 
 
@@ -402,6 +410,26 @@ def run_ours(args, rank, world, local_rank):
     n_pass = args.steps * passes
     value = world * B * n_pass / (elapsed_ms / 1e3)
 
+    # ---- optional timeline (nsys is not installed in this image): CUDA events around every stage of 8 consecutive passes
+    if args.trace:
+        barrier()
+        tev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(8)]
+        for e in tev:
+            one_pass(e)
+        join_consumer()
+        torch.cuda.synchronize()
+        mine = [[tev[0][0].elapsed_time(x) for x in e] for e in tev]  # ms since the first pass started, per rank
+        allr = [None] * world
+        if world > 1:
+            dist.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        if rank == 0:
+            labels = ["nms_peaks", "limb_score"] + (["limb_match", "assemble"] if args.unfused else ["match_assemble"]) + ["publish/gather", "end"]
+            json.dump({"what": "CUDA-event timestamps (ms since the rank's first pass began) at the start of each stage of 8 consecutive passes",
+                       "labels": labels, "n_gpus": world, "gather": gather_how, "ranks": allr}, open(args.trace, "w"))
+        barrier()
+
     # ---- correctness guards inside the bench: statuses clean, persons found, wire records = the device tables,
     # and at N > 1 what landed on rank 0 is byte for byte what every rank produced
     r_status = views["status"][:B].cpu().numpy()
@@ -566,6 +594,184 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+def make_network_outputs(args):
+    """Per scale: [B, 2, 50, h, w] float32 network outputs of the same synthetic people (synth.make_network_output)."""
+    from improved_body_parts_b200 import synth
+    cfg = CONFIGS[args.config]
+    bh, bw = cfg["net_hw"]
+    outs, crops = [], []
+    for f in cfg["scales"]:
+        h, w = int(round(bh * f)), int(round(bw * f))
+        outs.append(np.stack([synth.make_network_output(BASE_SEED + i, h, w, args.persons, body_scale=f, base_hw=(bh, bw))
+                              for i in range(args.batch)]))
+        crops.append((4 * h, 4 * w))  # no padding: the scaled image is a multiple of max_downsample
+    return outs, crops
+
+
+def run_pipeline(args, local_rank):
+    """Configurations whose input is the network output: one pass = spg_postnet (evaluate.py:126-161) + the grouping path."""
+    import torch
+
+    from improved_body_parts_b200 import skeleton
+    from improved_body_parts_b200.grouping import Grouper
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the grouping path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    H, W, B = args.H, args.W, args.batch
+    cfg = CONFIGS[args.config]
+    params = skeleton.default_params()
+    outs_np, crops = make_network_outputs(args)
+    outs_pin = [torch.from_numpy(o).pin_memory() for o in outs_np]
+    outs_d = [o.to(dev, non_blocking=True) for o in outs_pin]
+    single = len(outs_d) == 1
+    g = Grouper(max_batch=B, max_h=H, max_w=W, max_person_rows=CAP_ROWS, device=local_rank)
+    views = g.device_tensors()
+    heat_d = torch.empty((B, 18, H, W), dtype=torch.float32, device=dev)
+    paf_d = torch.empty((B, 30, H, W), dtype=torch.float32 if single else torch.float64, device=dev)
+    local_wire = torch.zeros((B, g.wire_record_bytes(CAP_ROWS)), dtype=torch.uint8, device=dev)
+    g.set_wire_output(local_wire.data_ptr(), 0, CAP_ROWS)
+    stream = torch.cuda.current_stream()
+    stages = [("postnet_kernel", lambda: g.postnet(outs_d, crops, (H, W), heat_out=heat_d, paf_out=paf_d)),
+              ("nms", lambda: g.nms_peaks(heat_d, params)),
+              ("score", lambda: g.limb_score(paf_d, H, params, paf_as_f64=single)),
+              ("match_assemble", lambda: g.match_assemble(B, params))]
+
+    def one_pass(evs=None, first=0):
+        for i, (_, fn) in enumerate(stages[first:]):
+            if evs: evs[i].record(stream)
+            fn()
+        if evs: evs[len(stages) - first].record(stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(4):
+        one_pass()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    passes = args.passes or max(1, min(64, math.ceil(100.0 / (args.steps * e0.elapsed_time(e1) / 4))))
+    for _ in range(max(args.warmup, 3) * passes):
+        one_pass()
+    torch.cuda.synchronize()
+
+    def timed(first):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        a.record(stream)
+        for k in range(args.steps):
+            for p in range(passes):
+                one_pass(evs[k] if p == 0 else None, first)
+        b.record(stream)
+        torch.cuda.synchronize()
+        sampler.window(w0, time.time())
+        ms = [statistics.fmean(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(len(stages) - first)]
+        return a.elapsed_time(b), ms
+
+    l0 = g.launch_count
+    elapsed_ms, stage_ms = timed(0)          # value: post-network stage + grouping
+    launches = g.launch_count - l0
+    group_ms, _ = timed(1)                   # the grouping stages alone on the resident maps
+    n_pass = args.steps * passes
+    value = B * n_pass / (elapsed_ms / 1e3)
+    r_status = views["status"][:B].cpu().numpy()
+    r_np = views["n_persons"][:B].cpu().numpy()
+    assert (r_status == 0).all(), f"status flags set: {np.unique(r_status)}"
+    assert r_np.min() > 0, "no persons found -- the timed path did no work"
+
+    # ---- e2e: pinned HOST network outputs -> H2D -> postnet -> grouping -> person lists on the host, every step
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    host_out = {k: torch.empty_like(views[k][:B], device="cpu").pin_memory() for k in ("n_persons", "people_xy", "people_score", "status")}
+    stage_in = [torch.empty_like(o) for o in outs_d]
+
+    def host_call():
+        for dst, src in zip(stage_in, outs_pin):
+            dst.copy_(src, non_blocking=True)
+        g.postnet(stage_in, crops, (H, W), heat_out=heat_d, paf_out=paf_d)
+        g.group_device(heat_d, paf_d, H, params, paf_as_f64=single)
+        for k, t in host_out.items():
+            t.copy_(views[k][:B], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        host_call()
+    w0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_call()
+    e2e_s = time.perf_counter() - t0
+    sampler.window(w0, time.time())
+    assert np.array_equal(host_out["n_persons"].numpy(), r_np)
+    h2d = sum(o.nbytes for o in outs_np)
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    clocks = sampler.stop()
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    esz = 4 if single else 8
+    ns = len(outs_d)
+    net_read = sum(B * 2 * 48 * o.shape[3] * o.shape[4] * 4 for o in outs_d)
+    plane = B * H * W
+    if single:
+        post_bytes = net_read + plane * (18 * 4 + 30 * 4)
+    else:  # float64 accumulators: written by every scale, read back by all but the first; float32 keypoint maps once
+        post_bytes = net_read + plane * 48 * 8 * ns + plane * 48 * 8 * (ns - 1) + plane * 18 * 4
+    alg = [post_bytes, plane * 18 * 4, plane * 30 * esz, None]
+    names = ["postnet_kernel"] + [n for n in g.stage_kernels() if n][:3]
+    kernels = {}
+    for i, nme in enumerate(names):
+        kernels[nme] = {"ms": stage_ms[i], "algorithmic_GBps": alg[i] / (stage_ms[i] * 1e-3) / 1e9 if alg[i] else None,
+                        "frac_of_hbm_peak": alg[i] / (stage_ms[i] * 1e-3) / 1e9 / hbm_peak if alg[i] else None}
+        if i == 0 and ns > 1:
+            kernels[nme]["launches_per_pass"] = ns
+    dom = max(range(len(names)), key=lambda i: stage_ms[i])
+    ach = (alg[dom] or sum(a for a in alg if a)) / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom]}
+    result = {
+        "metric": metric_name(args) + " (from the network output)", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "ms_per_pass": elapsed_ms / n_pass,
+        "timed_region_ms": elapsed_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"f32 network output; {cfg['paf']} body-part maps, f32 keypoint maps; f64 coordinates/scores", "data": "synthetic",
+        "config": dict(workload_config(args, 1, passes), network_output=[list(o.shape) for o in outs_d], crops=crops),
+        "grouping_only": {"value": B * n_pass / (group_ms / 1e3), "unit": UNIT, "ms_per_pass": group_ms / n_pass,
+                          "note": "the three grouping kernels alone on the resident maps the post-network stage produced"},
+        "e2e": {"value": B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "Grouper.postnet + Grouper.group_device on pinned host network outputs, person lists copied back; one call per step"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "persons_found_per_image": float(r_np.mean()),
+    }
+    if not args.no_cpu_baseline:
+        from oracle import grouping_port as gp
+        from oracle import postnet_port as pp
+        n_cpu = 2 if H > 128 else 16
+        t0 = time.perf_counter()
+        found = []
+        for i in range(n_cpu):
+            ha, pa = np.zeros((H, W, 18)), np.zeros((H, W, 30))
+            for o, (ch, cw) in zip(outs_np, crops):
+                hm, pf = pp.post_network_scale(o[i], 4, (ch, cw), [0, 0, 0, 0], (H, W), 30, 48, skeleton.FLIP_PAF_ORD, skeleton.FLIP_HEAT_ORD[:18])
+                ha, pa = pp.accumulate(ha, hm, ns), pp.accumulate(pa, pf, ns)
+            found.append(gp.group_image(np.ascontiguousarray(ha.transpose(2, 0, 1)).astype(np.float32),
+                                        np.ascontiguousarray(pa.transpose(2, 0, 1)), H, params, skeleton.LIMBS)[3].shape[0])
+        dt = time.perf_counter() - t0
+        assert found == [int(v) for v in r_np[:n_cpu]], f"CPU pipeline and CUDA pipeline disagree on person counts: {found} vs {r_np[:n_cpu]}"
+        result["cpu_baseline"] = {"value": n_cpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                  "sample": f"first {n_cpu} images: oracle/postnet_port.py + oracle/grouping_port.py (Python/numpy ports "
+                                            f"of evaluate.py:126-161 and :169-498), one process, {dt:.1f} s"}
+    print(json.dumps(result), flush=True)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -575,6 +781,11 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} needs `python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...`")
     if args.impl == "reference":
         run_reference(args, rank, world)  # pure Python: builds and loads nothing of the product
+    elif "scales" in CONFIGS[args.config]:
+        if world > 1:
+            raise SystemExit("the pipeline configurations are single-GPU configurations")
+        build_once()
+        run_pipeline(args, local_rank)
     else:
         build_once()
         run_ours(args, rank, world, local_rank)

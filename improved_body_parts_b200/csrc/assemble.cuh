@@ -43,7 +43,7 @@ struct AssembleArgs {
 
 constexpr int kAssembleThreads = 32;
 
-inline size_t assemble_smem_bytes(int K, int capP, int capR) {
+__host__ __device__ inline size_t assemble_smem_bytes(int K, int capP, int capR) {
     size_t b = (size_t)K * capR * sizeof(double)      // sc
                + 2 * (size_t)capR * sizeof(double)    // total, maxlen
                + (size_t)K * capR * sizeof(int)       // id
@@ -67,8 +67,56 @@ struct PersonTable {
     float *ps;
     short *owner;
     unsigned char *alive;
+    const double *px, *py;  // refined peak coordinates [K][capP]: global memory, or the fused kernel's shared-memory copy
     int K, capP, capR;
 };
+
+// carve the person table out of shared memory
+__device__ __forceinline__ PersonTable make_person_table(unsigned char *table_base, int K, int capP, int capR) {
+    PersonTable t;
+    t.K = K; t.capP = capP; t.capR = capR;
+    t.sc = reinterpret_cast<double *>(table_base);
+    t.total = t.sc + (size_t)K * capR;
+    t.maxlen = t.total + capR;
+    t.id = reinterpret_cast<int *>(t.maxlen + capR);
+    t.cnt = t.id + (size_t)K * capR;
+    t.touch = t.cnt + capR;
+    t.birth = t.touch + capR;
+    t.mask = reinterpret_cast<uint32_t *>(t.birth + capR);
+    t.ps = reinterpret_cast<float *>(t.mask + capR);
+    t.off = reinterpret_cast<int *>(t.ps + (size_t)K * capP);
+    t.owner = reinterpret_cast<short *>(t.off + (K + 1));
+    t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
+    t.px = t.py = nullptr;
+    return t;
+}
+
+// peak scores, owner map, row flags and part offsets of image n, by `nthreads` cooperating threads (one warp in the
+// stand-alone kernel, the whole CTA in the fused one); s_xy != nullptr: also stage the refined coordinates (the output
+// phase gathers 17 of them per person -- from L2 that was 20 % of the stand-alone kernel's time)
+__device__ __forceinline__ void init_person_table(const PersonTable &t, const Workspace &ws, int n, int tid, int nthreads, double *s_xy) {
+    const int K = t.K, capP = t.capP, capR = t.capR;
+    if (tid == 0) {
+        int acc = 0;
+        for (int c = 0; c < K; c++) {
+            t.off[c] = acc;
+            acc += min(ws.peak_count[(size_t)n * K + c], capP);
+        }
+        t.off[K] = acc;
+    }
+    for (int i = tid; i < K * capP; i += nthreads) {
+        t.ps[i] = ws.peak_score[(size_t)n * K * capP + i];
+        t.owner[i] = -1;
+        if (s_xy) {
+            s_xy[i] = ws.peak_x[(size_t)n * K * capP + i];
+            s_xy[(size_t)K * capP + i] = ws.peak_y[(size_t)n * K * capP + i];
+        }
+    }
+    for (int i = tid; i < capR; i += nthreads) {
+        t.touch[i] = 0x7fffffff;
+        t.alive[i] = 0;
+    }
+}
 
 // The reference's per-connection transition (:320-488), executed by ONE thread.  `new_row` is the row index to
 // use if the connection matches nothing, `birth` its stamp.  Returns status flags.
@@ -194,20 +242,14 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
     int *s_cc = reinterpret_cast<int *>(s_cij + LC);
     unsigned char *table_base = smem_raw + assemble_conn_bytes(L, capP);
 
-    PersonTable t;
-    t.K = K; t.capP = capP; t.capR = capR;
-    t.sc = reinterpret_cast<double *>(table_base);
-    t.total = t.sc + (size_t)K * capR;
-    t.maxlen = t.total + capR;
-    t.id = reinterpret_cast<int *>(t.maxlen + capR);
-    t.cnt = t.id + (size_t)K * capR;
-    t.touch = t.cnt + capR;
-    t.birth = t.touch + capR;
-    t.mask = reinterpret_cast<uint32_t *>(t.birth + capR);
-    t.ps = reinterpret_cast<float *>(t.mask + capR);
-    t.off = reinterpret_cast<int *>(t.ps + (size_t)K * capP);
-    t.owner = reinterpret_cast<short *>(t.off + (K + 1));
-    t.alive = reinterpret_cast<unsigned char *>(t.owner + (size_t)K * capP);
+    PersonTable t = make_person_table(table_base, K, capP, capR);
+    if (FUSED) {  // the CTA staged the coordinates behind the person table (match_assemble_kernel)
+        t.px = reinterpret_cast<const double *>(table_base + assemble_smem_bytes(K, capP, capR));
+        t.py = t.px + (size_t)K * capP;
+    } else {
+        t.px = ws.peak_x + (size_t)n * K * capP;
+        t.py = ws.peak_y + (size_t)n * K * capP;
+    }
 
     // Everything this image needs from global memory is fetched up front -- the connection tables by the bulk-copy
     // engine -- so that the serial limb loop below never waits on L2.
@@ -232,22 +274,7 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
     }
     if (!FUSED)
         for (int k = lane; k < L; k += 32) s_cc[k] = ws.conn_count[(size_t)n * L + k];
-    if (lane == 0) {
-        int acc = 0;
-        for (int c = 0; c < K; c++) {
-            t.off[c] = acc;
-            acc += min(ws.peak_count[(size_t)n * K + c], capP);
-        }
-        t.off[K] = acc;
-    }
-    for (int i = lane; i < K * capP; i += 32) {
-        t.ps[i] = ws.peak_score[(size_t)n * K * capP + i];
-        t.owner[i] = -1;
-    }
-    for (int i = lane; i < capR; i += 32) {
-        t.touch[i] = 0x7fffffff;
-        t.alive[i] = 0;
-    }
+    if (!FUSED) init_person_table(t, ws, n, lane, 32, nullptr);  // fused: done by the whole CTA before the roles split
     __syncwarp();
     if (!FUSED && a.use_bulk) mbar_wait(&bar, 0);
 
@@ -322,8 +349,7 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
     double *g_subset = ws.subset + (size_t)n * capR * RS * 2;
     double *g_xy = ws.people_xy + (size_t)n * capR * J * 2;
     double *g_score = ws.people_score + (size_t)n * capR;
-    const double *g_px = ws.peak_x + (size_t)n * K * capP;
-    const double *g_py = ws.peak_y + (size_t)n * K * capP;
+    const double *g_px = t.px, *g_py = t.py;
     // wire record (include/spgroup.h): rows are staged in shared memory -- the connection tables are dead by now -- and
     // leave in one coalesced copy, so a record in a peer GPU's memory costs a few 128-byte NVLink writes per image
     const int WR = 2 * J + 2;  // x,y per joint, person score, presence mask

@@ -19,6 +19,10 @@ namespace spg {
 constexpr int kMAMatchWarps = 7;
 constexpr int kMAThreads = 32 * (1 + kMAMatchWarps);
 
+inline size_t match_assemble_smem_bytes(int K, int L, int capP, int capR) {  // tables + person table + staged coordinates
+    return assemble_conn_bytes(L, capP) + assemble_smem_bytes(K, capP, capR) + 2 * (size_t)K * capP * sizeof(double);
+}
+
 __global__ void __launch_bounds__(kMAThreads) match_assemble_kernel(AssembleArgs a, int keys_valid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;  // unused in the fused form (the matchers fill the tables)
@@ -29,6 +33,11 @@ __global__ void __launch_bounds__(kMAThreads) match_assemble_kernel(AssembleArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = ws.L, capP = ws.capP;
     if (tid < L) s_ready[tid] = 0;
+    {   // CTA-wide prologue: person table + the image's refined coordinates into shared memory
+        unsigned char *table_base = smem_raw + assemble_conn_bytes(L, capP);
+        const PersonTable t = make_person_table(table_base, ws.K, capP, ws.capR);
+        init_person_table(t, ws, n, tid, kMAThreads, reinterpret_cast<double *>(table_base + assemble_smem_bytes(ws.K, capP, ws.capR)));
+    }
     __syncthreads();
     if (warp == 0) {
         assemble_image<true>(a, smem_raw, bar, n, blockIdx.x, lane, s_ready);

@@ -52,6 +52,7 @@ struct spg_handle {
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
     int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
+    int screen_ilp = 1;   // pairs a screener lane of the persistent limb_score handles at once (SPG_SCREEN_ILP = 1 | 2)
     int wait_ns = 0;      // persistent kernels: explicit back-off between mbarrier polls (SPG_WAIT_NS; 0 = suspend-hint wait)
     int fuse_ma = 1;      // whole-path calls run the fused match+assemble kernel (SPG_FUSE_MA=0: the two kernels back to back)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
@@ -167,9 +168,15 @@ int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
         persist_smem_bytes(plane_bytes, h->ws.capP) <= h->smem_optin) {
         // one resident CTA per SM walking a ring of 3 plane slots (loader / screeners / scorers)
         const size_t smem = persist_smem_bytes(plane_bytes, h->ws.capP);
-        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        limb_score_persist_kernel<TA><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
-        h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float>" : "limb_score_persist_kernel<double>";
+        if (h->screen_ilp == 2) {
+            SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_persist_kernel<TA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+            limb_score_persist_kernel<TA, 2><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+            h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float,2>" : "limb_score_persist_kernel<double,2>";
+        } else {
+            SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_persist_kernel<TA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+            limb_score_persist_kernel<TA, 1><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+            h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float,1>" : "limb_score_persist_kernel<double,1>";
+        }
     } else if (aligned && staged <= h->smem_optin) {
         SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_kernel<T, true, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged)));
         limb_score_kernel<T, true, TA><<<grid, kScoreThreads, staged, st>>>(a);
@@ -267,8 +274,12 @@ int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, c
     a.ws = h->ws;
     a.ws.wire_first += base;
     a.use_bulk = 0;
-    const size_t smem = assemble_smem_bytes(h->ws.K, h->ws.capP, h->ws.capR) + assemble_conn_bytes(h->ws.L, h->ws.capP);
-    if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "capacities need %zu B of shared memory in match_assemble (limit %zu)", smem, h->smem_optin);
+    const size_t smem = match_assemble_smem_bytes(h->ws.K, h->ws.L, h->ws.capP, h->ws.capR);
+    if (smem > h->smem_optin) {  // very large capacities: the two stand-alone kernels need less shared memory
+        int rc;
+        if ((rc = launch_match(h, base, n, st))) return rc;
+        return launch_assemble(h, base, n, p, st);
+    }
     SPG_CUDA(h, cudaFuncSetAttribute(match_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_assemble_kernel<<<n, kMAThreads, smem, st>>>(a, h->cand_dtype == SPG_F32);
     h->stage_kernel[2] = "match_assemble_kernel";
@@ -347,6 +358,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
+    if (const char *e = getenv("SPG_SCREEN_ILP")) h->screen_ilp = atoi(e) == 2 ? 2 : 1;
     if (const char *e = getenv("SPG_WAIT_NS")) h->wait_ns = std::max(0, std::min(100000, atoi(e)));
     if (const char *e = getenv("SPG_FUSE_MA")) h->fuse_ma = !(e[0] == '0');
     if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener

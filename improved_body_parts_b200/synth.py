@@ -177,3 +177,26 @@ def make_batch(base_seed: int, n: int, H: int = 128, W: int = 128, persons: int 
     for i in range(n):
         heat[i], paf[i] = make_image(base_seed + i, H, W, persons, **kw)
     return heat, paf
+
+
+def make_network_output(seed: int, h: int, w: int, persons: int, *, body_scale: float = 1.0, noise: float = 0.004,
+                        base_hw: Tuple[int, int] = None, scale_range: Tuple[float, float] = (0.8, 1.3)) -> np.ndarray:
+    """What the IMHN would answer for (image, mirrored image): ``[2, 50, h, w]`` float32 in the network's channel
+    layout (body parts 0..29, keypoints 30..47, background 48..49; config/config.py:101-103).
+
+    The first map holds the synthetic maps, the second a mirrored, channel-permuted copy plus a little noise, so that the
+    flip ensemble (evaluate.py:139-140) has something to average.  ``body_scale`` renders the SAME skeletons (drawn for a
+    ``base_hw`` map, default ``h / body_scale``) at another resolution -- the multi-scale search of predict()."""
+    from .skeleton import FLIP_HEAT_ORD, FLIP_PAF_ORD
+    rng = np.random.default_rng(seed)
+    bh, bw = base_hw if base_hw is not None else (int(round(h / body_scale)), int(round(w / body_scale)))
+    joints = sample_skeletons(rng, persons, bh, bw, scale_range=scale_range) * body_scale
+    visible = np.ones((persons, NUM_PARTS), bool)
+    heat, paf = render(joints, visible, h, w, np.random.default_rng(seed + 1), sigma_scale=body_scale)
+    out = np.zeros((2, 50, h, w), np.float32)
+    out[0, :30], out[0, 30:48] = paf, heat
+    out[0, 48:] = rng.random((2, h, w), dtype=np.float32)
+    out[1, :30] = paf[np.argsort(FLIP_PAF_ORD)][..., ::-1]
+    out[1, 30:48] = heat[np.argsort(FLIP_HEAT_ORD[:NUM_PARTS])][..., ::-1]
+    out[1] += (rng.random((50, h, w), dtype=np.float32) - 0.5) * np.float32(noise)
+    return out

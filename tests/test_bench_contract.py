@@ -37,3 +37,23 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "1", "--batch", "4")
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_loads_nothing_of_the_product_and_reports_its_cpu_budget():
+    """the reference arm used to dlopen libspgroup.so (through build()) and sized its pool with
+    os.cpu_count(), which ignores the cgroup quota / affinity of the lease."""
+    code = (
+        "import runpy, sys, os\n"
+        f"sys.argv = [{os.path.join(ROOT, 'bench.py')!r}, '--impl', 'reference', '--steps', '1', '--warmup', '1', '--batch', '4', '--persons', '5']\n"
+        f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+        "mods = [m for m in sys.modules if m in ('improved_body_parts_b200.grouping', 'improved_body_parts_b200.dropin', '__graft_entry__')]\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "print('CHECK', mods, maps.count('libspgroup'))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    check = next(l for l in r.stdout.splitlines() if l.startswith("CHECK"))
+    assert check == "CHECK [] 0", check  # torch (and its own CUDA runtime) may be there for get_num_threads(); nothing of ours
+    d = json.loads(next(l for l in r.stdout.splitlines() if l.startswith("{")))
+    cb = d["cpu_baseline"]
+    assert cb["cores"] == cb["cpus"]["usable"] <= cb["cpus"]["affinity"] and cb["single_process"]["value"] > 0
+    assert cb["cpus"]["usable"] == len(os.sched_getaffinity(0)) or cb["cpus"]["cgroup_quota_cpus"] is not None

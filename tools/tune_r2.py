@@ -29,7 +29,7 @@ def timeit(fn, iters=30):
 
 
 def measure(env):
-    for k in ("SPG_WAIT_NS", "SPG_EXACT_WARPS", "SPG_FUSE_MA", "SPG_PERSIST"):
+    for k in ("SPG_WAIT_NS", "SPG_EXACT_WARPS", "SPG_FUSE_MA", "SPG_PERSIST", "SPG_SCREEN_ILP"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     g = Grouper(max_batch=NB, max_person_rows=64)
@@ -48,5 +48,7 @@ for w in (25, 50, 100, 200, 400, 800, 1600):
     measure({"SPG_WAIT_NS": w})
 for ew in (10, 14):
     measure({"SPG_EXACT_WARPS": ew})
-measure({"SPG_FUSE_MA": 0})
+for ew in (12, 14, 16, 18):
+    measure({"SPG_SCREEN_ILP": 2, "SPG_EXACT_WARPS": ew})
+measure({"SPG_SCREEN_ILP": 2, "SPG_EXACT_WARPS": 16, "SPG_WAIT_NS": 100})
 measure({})
