@@ -78,6 +78,50 @@ __device__ __forceinline__ int match_rounds_keys(uint32_t *o_ij, double *o_norm,
     return m;
 }
 
+// The same rounds for f64 priorities (f64 planes, or f32 planes evaluated in f64): the key is the order-preserving 64-bit
+// image of the priority plus the 32-bit tie-break, three REDUX per round.
+template <int NS>
+__device__ __forceinline__ int match_rounds_f64(const Workspace &ws, size_t cbase, uint32_t *o_ij, double *o_norm, int nC, int lim, int lane) {
+    unsigned long long r_key[NS];  // ordered priority bits; 0 = dead / absent
+    uint32_t r_tie[NS];            // ~((i << 16) | j): larger = earlier in generation order
+#pragma unroll
+    for (int r = 0; r < NS; r++) {
+        const int cidx = lane + 32 * r;
+        const bool ok = cidx < nC;
+        r_key[r] = ok ? ordered_bits(ws.cand_prio[cbase + cidx]) : 0ull;
+        r_tie[r] = ok ? ~ws.cand_ij[cbase + cidx] : 0u;
+    }
+    int m = 0;
+    while (m < lim) {
+        unsigned long long bk = 0ull;
+        uint32_t bt = 0u;
+        int br = -1;
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            const bool better = r_key[r] > bk || (r_key[r] == bk && r_key[r] != 0ull && r_tie[r] > bt);
+            if (better) { bk = r_key[r]; bt = r_tie[r]; br = r; }
+        }
+        const uint32_t hi = (uint32_t)(bk >> 32), lo = (uint32_t)bk;
+        const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+        if (mhi == 0u) break;
+        const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        const bool tied = (hi == mhi) && (lo == mlo);
+        const uint32_t mt = __reduce_max_sync(0xffffffffu, tied ? bt : 0u);
+        const uint32_t wij = ~mt;
+        if (tied && bt == mt) {
+            o_ij[m] = wij;
+            reinterpret_cast<int *>(o_norm + m)[0] = lane + 32 * br;  // candidate index, replaced by the norm afterwards
+        }
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            const uint32_t x = ~r_tie[r] ^ wij;
+            if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
+        }
+        m++;
+    }
+    return m;
+}
+
 // The greedy matching of ONE (image, limb) by one warp.  Rows go to o_ij / o_score / o_norm (global memory in the
 // stand-alone kernel, shared memory in the fused match+assemble kernel); returns the number of connections, -1 for
 // special_k (evaluate.py:272-274).
@@ -139,39 +183,24 @@ __device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int
             o_norm[c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
         }
     } else if (nC <= 32 * kMatchRegF64) {
-        // ---- register path, f64 planes: (ordered f64 priority, tie-break) -------------------------------
-        unsigned long long r_key[kMatchRegF64];  // ordered priority bits; 0 = dead / absent
-        uint32_t r_tie[kMatchRegF64];            // ~((i << 16) | j): larger = earlier in generation order
-#pragma unroll
-        for (int r = 0; r < kMatchRegF64; r++) {
-            const int cidx = lane + 32 * r;
-            const bool ok = cidx < nC;
-            r_key[r] = ok ? ordered_bits(ws.cand_prio[cbase + cidx]) : 0ull;
-            r_tie[r] = ok ? ~ws.cand_ij[cbase + cidx] : 0u;
+        // ---- register path, f64 priorities: (ordered f64 priority bits, tie-break), specialised on the slot count -----
+        switch (nslots) {
+            case 0: break;
+            case 1: m = match_rounds_f64<1>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 2: m = match_rounds_f64<2>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 3: m = match_rounds_f64<3>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 4: m = match_rounds_f64<4>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 5: case 6: m = match_rounds_f64<6>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            default: m = match_rounds_f64<kMatchRegF64>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
         }
-        while (m < lim) {
-            unsigned long long bk = 0ull;
-            uint32_t bt = 0u;
-            int br = -1;
-#pragma unroll
-            for (int r = 0; r < kMatchRegF64; r++) {
-                const bool better = r_key[r] > bk || (r_key[r] == bk && r_key[r] != 0ull && r_tie[r] > bt);
-                if (better) { bk = r_key[r]; bt = r_tie[r]; br = r; }
-            }
-            const uint32_t hi = (uint32_t)(bk >> 32), lo = (uint32_t)bk;
-            const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-            if (mhi == 0u) break;
-            const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-            const bool tied = (hi == mhi) && (lo == mlo);
-            const uint32_t mt = __reduce_max_sync(0xffffffffu, tied ? bt : 0u);
-            const uint32_t wij = ~mt;
-            if (tied && bt == mt) emit(m, wij, lane + 32 * br);
-#pragma unroll
-            for (int r = 0; r < kMatchRegF64; r++) {
-                const uint32_t x = ~r_tie[r] ^ wij;
-                if ((x & 0xffff0000u) == 0u || (x & 0x0000ffffu) == 0u) r_key[r] = 0ull;
-            }
-            m++;
+        __syncwarp();
+        for (int c = lane; c < m; c += 32) {  // scores and limb lengths in parallel, as in the f32 path
+            const uint32_t ij = o_ij[c];
+            o_score[c] = ws.cand_score[cbase + reinterpret_cast<const int *>(o_norm + c)[0]];
+            const int i = (int)(ij >> 16), j = (int)(ij & 0xffff);
+            const double vx = __dsub_rn(ws.peak_x[baseB + j], ws.peak_x[baseA + i]);
+            const double vy = __dsub_rn(ws.peak_y[baseB + j], ws.peak_y[baseA + i]);
+            o_norm[c] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
         }
     } else {
         // ---- generic path: re-read the list from L2 every round, 128-bit used masks -------------------
