@@ -306,6 +306,15 @@ __global__ void wire_signal_kernel(unsigned long long *word, unsigned long long 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(word), "l"(value) : "memory");
 }
 
+struct WireWords {
+    unsigned long long *p[32];
+    int n;
+};
+__global__ void wire_signal_many_kernel(WireWords w, unsigned long long value) {
+    __threadfence_system();
+    if ((int)threadIdx.x < w.n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(w.p[threadIdx.x]), "l"(value) : "memory");
+}
+
 __global__ void wire_wait_kernel(const unsigned long long *word, unsigned long long value) {
     unsigned long long v;
     do {
@@ -505,6 +514,19 @@ int spg_wire_signal(int32_t device, uint64_t *word_dev, uint64_t value, void *st
     DeviceGuard guard(device);
     wire_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(word_dev), value);
     return cudaGetLastError() == cudaSuccess ? SPG_OK : fail(nullptr, SPG_E_CUDA, "wire_signal launch failed");
+}
+
+int spg_wire_signal_many(int32_t device, uint64_t *const *words_dev, int32_t n_words, uint64_t value, void *stream) {
+    if (!words_dev || n_words < 1 || n_words > 32) return SPG_E_INVALID;
+    DeviceGuard guard(device);
+    WireWords w{};
+    w.n = n_words;
+    for (int i = 0; i < n_words; i++) {
+        if (!words_dev[i]) return SPG_E_INVALID;
+        w.p[i] = reinterpret_cast<unsigned long long *>(words_dev[i]);
+    }
+    wire_signal_many_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(w, value);
+    return cudaGetLastError() == cudaSuccess ? SPG_OK : fail(nullptr, SPG_E_CUDA, "wire_signal_many launch failed");
 }
 
 int spg_wire_wait(int32_t device, const uint64_t *word_dev, uint64_t value, void *stream) {

@@ -30,7 +30,7 @@ EXPORTS = (
     "spg_assemble", "spg_upload_peaks", "spg_upload_connections", "spg_download_peaks", "spg_download_connections",
     "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel", "spg_wire_record_bytes",
     "spg_set_wire_output", "spg_wire_create", "spg_wire_open", "spg_wire_close", "spg_wire_destroy", "spg_wire_signal",
-    "spg_wire_wait", "spg_postnet", "spg_match_assemble")
+    "spg_wire_wait", "spg_postnet", "spg_match_assemble", "spg_wire_signal_many")
 
 
 class GroupingError(RuntimeError):
@@ -230,6 +230,14 @@ def wire_signal(device: int, word_ptr: int, value: int, stream) -> None:
     if load_library().spg_wire_signal(C.c_int32(device), C.c_void_p(word_ptr), C.c_uint64(value),
                                       C.c_void_p(int(getattr(stream, "cuda_stream", stream)))) != 0:
         raise GroupingError("spg_wire_signal failed")
+
+
+def wire_signal_many(device: int, word_ptrs: Sequence[int], value: int, stream) -> None:
+    """One launch that release-stores ``value`` into every word of ``word_ptrs`` (<= 32, local or peer memory)."""
+    arr = (C.c_void_p * len(word_ptrs))(*[C.c_void_p(p) for p in word_ptrs])
+    if load_library().spg_wire_signal_many(C.c_int32(device), arr, C.c_int32(len(word_ptrs)), C.c_uint64(value),
+                                           C.c_void_p(int(getattr(stream, "cuda_stream", stream)))) != 0:
+        raise GroupingError("spg_wire_signal_many failed")
 
 
 def wire_wait(device: int, word_ptr: int, value: int, stream) -> None:

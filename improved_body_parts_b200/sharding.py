@@ -106,7 +106,7 @@ class PeerWireSink:
 
     HEADER = 4096
 
-    def __init__(self, n_local: int, record_bytes: int, device: int, dst: int = 0, group=None, slots: int = 2):
+    def __init__(self, n_local: int, record_bytes: int, device: int, dst: int = 0, group=None, slots: int = 3):
         import torch.distributed as dist
 
         from . import grouping as G
@@ -158,7 +158,8 @@ class PeerWireSink:
 
     # -- producer side (every rank) -----------------------------------------------------------------
     def begin(self, step: int, stream) -> int:
-        """Wait until the generation ``step`` will overwrite has been consumed; returns this rank's slice address."""
+        """Make ``stream`` wait until the generation ``step`` will overwrite has been consumed (call it right before
+        the assemble stage is launched -- earlier kernels of the step do not need the slot); returns this rank's slice address."""
         if step >= self.slots:
             self.G.wire_wait(self.device, self._mail_local, step - self.slots + 1, stream)
         return self._sink + self.HEADER + (step % self.slots) * self.gen_bytes + self.offset * self.record_bytes
@@ -178,8 +179,8 @@ class PeerWireSink:
     def release(self, step: int, stream) -> None:
         """``dst``: the generation of ``step`` has been consumed; let the producers reuse it."""
         assert self.rank == self.dst
-        for r in range(self.world):
-            self.G.wire_signal(self.device, self._mail[r], step + 1, stream)
+        for lo in range(0, self.world, 32):
+            self.G.wire_signal_many(self.device, self._mail[lo:lo + 32], step + 1, stream)
 
     def close(self) -> None:
         """Collective: unmap the peers' buffers, then (after a barrier: an exporter must outlive its importers) free ours."""

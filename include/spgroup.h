@@ -230,6 +230,8 @@ int spg_wire_destroy(int32_t device, void *dev_ptr);
 /* release-store `value` into a 64-bit word (local or peer memory) once everything earlier on `stream` has
  * completed: a one-thread kernel (fence.sys + st.release.sys).  The producer's "my records have landed". */
 int spg_wire_signal(int32_t device, uint64_t *word_dev, uint64_t value, void *stream);
+/* the same value into up to 32 words (each local or peer memory) with ONE launch: the consumer's acknowledgement to all ranks */
+int spg_wire_signal_many(int32_t device, uint64_t *const *words_dev, int32_t n_words, uint64_t value, void *stream);
 /* make `stream` wait until *word_dev >= value.  `word_dev` must be LOCAL device memory: the wait is a stream
  * memory operation (cuStreamWaitValue64), executed by the copy/compute front end -- no kernel sits on an SM
  * spinning, so it cannot collide with the persistent kernels that own every SM.  */
