@@ -609,17 +609,23 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
         a.sx2 = 1.0 / ((double)W / (double)sc.crop_w);
         a.sy2 = 1.0 / ((double)H / (double)sc.crop_h);
         // output tile: as large as the shared-memory tiles of the intermediate / source allow
-        auto tile_dim = [&](double s2, double s1, int cap1, int cap0, int maxd) {
-            const double c1 = std::min((double)cap1, ((double)cap0 - 7.0) / s1) - 7.0;  // intermediate span allowed
+        const bool fast = d->stride == 4;  // the reference's model: four-phase kernel; other strides: table-driven generic kernel
+        auto tile_dim = [&](double s2, double s1, int cap1, int cap0, int maxd, double margin) {
+            const double c1 = std::min((double)cap1, ((double)cap0 - 7.0) / s1) - margin;  // intermediate span allowed
             return std::max(1, std::min(maxd, (int)(c1 / std::max(s2, 1e-6))));
         };
-        a.tile_w = tile_dim(a.sx2, a.sx1, kPostC1, kPostCS, kPostTW);
-        a.tile_h = tile_dim(a.sy2, a.sy1, kPostR1, kPostRS, kPostTH);
+        a.tile_w = fast ? tile_dim(a.sx2, a.sx1, kPostF_C1, kPostCS, kPostTW, 13.0) : tile_dim(a.sx2, a.sx1, kPostC1, kPostCS, kPostTW, 7.0);
+        a.tile_h = fast ? tile_dim(a.sy2, a.sy1, kPostF_R1, kPostRS, kPostTH, 13.0) : tile_dim(a.sy2, a.sy1, kPostR1, kPostRS, kPostTH, 7.0);
         a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
         a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
         if ((long long)a.tiles_x * a.tiles_y > 0x7fffffffLL || n > 65535) return fail(h, SPG_E_INVALID, "postnet grid too large");
         dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)a.n_out, (unsigned)n);
-        postnet_kernel<<<grid, kPostThreads, 0, st>>>(a);
+        if (fast) {
+            SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostF_SmemBytes));
+            postnet_kernel<<<grid, kPostThreads, kPostF_SmemBytes, st>>>(a);
+        } else {
+            postnet_generic_kernel<<<grid, kPostThreads, 0, st>>>(a);
+        }
         h->launches++;
         SPG_CUDA(h, cudaGetLastError());
     }

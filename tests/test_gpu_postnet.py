@@ -69,6 +69,9 @@ CASES = {
     "upscale_ratio_0.6": ([(16, 32)], [(60, 110)], (100, 183)),            # image larger than the network input
     "odd_sizes": ([(19, 23)], [(70, 89)], (131, 167)),
     "three_scales": ([(16, 16), (32, 32), (64, 64)], [(64, 64), (128, 128), (250, 250)], (125, 125)),
+    "many_tiles_ratio_1.33": ([(48, 64)], [(192, 250)], (144, 188)),       # several tiles per axis, inner and border ones
+    "ratio_2_and_0.5": ([(64, 32)], [(256, 128)], (128, 256)),             # crop twice / half the image
+    "tiny": ([(3, 5)], [(9, 17)], (7, 23)),
 }
 
 
@@ -98,6 +101,21 @@ def test_postnet_maps_are_the_checkers_maps(env, name, net_dtype):
     finally:
         g.close()
     assert np.abs(ref_heat).max() > 0.3 and np.abs(ref_paf).max() > 0.3
+
+
+@pytest.mark.parametrize("stride,hw,crop,image", [(2, (40, 48), (76, 90), (61, 77)), (8, (12, 16), (90, 120), (90, 120)), (4, (24, 24), (96, 96), (96, 96))])
+def test_other_strides_take_the_generic_kernel(env, stride, hw, crop, image):
+    """stride 4 (the reference's model) runs the four-phase kernel; any other stride the table-driven generic one.  Both
+    against the checker, bit for bit."""
+    t = env.torch
+    out = _network_like_output(env, 321 + stride, 2, hw[0], hw[1], 3)
+    ref_heat, ref_paf = _port_maps(env, [out], [crop], stride, image)
+    g = env.Grouper(max_batch=2, max_h=image[0], max_w=image[1])
+    try:
+        heat, paf = g.postnet([t.from_numpy(out).to(env.dev)], [crop], image, stride=stride, paf_dtype=t.float64)
+        assert np.array_equal(heat.cpu().numpy(), ref_heat.astype(np.float32)) and np.array_equal(paf.cpu().numpy(), ref_paf)
+    finally:
+        g.close()
 
 
 def test_network_tensor_is_consumed_in_place_with_strides(env):
