@@ -113,7 +113,8 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
                limbs: Sequence[Tuple[int, int]] = LIMBS, drop_prob: float = 0.0, plateau: int = 0, spikes: int = 0,
                colocate: int = 0, missing_parts: Sequence[int] = (), edge: bool = False, negative_bias: float = 0.0,
                stretch: int = 0, noise_levels: Optional[int] = None, heat_gain: float = 1.0, paf_gain: float = 1.0,
-               scale_range: Tuple[float, float] = (0.8, 1.3), sigma_scale: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
+               scale_range: Tuple[float, float] = (0.8, 1.3), sigma_scale: float = 1.0,
+               noise: float = NOISE_MAX) -> Tuple[np.ndarray, np.ndarray]:
     """One synthetic image.  ``seed`` fully determines the result for a given numpy build.
 
     Dirty knobs: ``drop_prob`` removes joints at random; ``plateau`` copies that many peak values onto a
@@ -124,7 +125,8 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
     ``negative_bias`` shifts the body-part maps down so some samples are negative;
     ``stretch`` moves that many wrists far away (long-limb rejects, evaluate.py:324,353,409);
     ``heat_gain`` / ``paf_gain`` scale the maps (weak persons that the final prune removes, :491-496);
-    ``scale_range`` / ``sigma_scale`` size the bodies and the blobs (4x for maps at image resolution, stride 4).
+    ``scale_range`` / ``sigma_scale`` size the bodies and the blobs (4x for maps at image resolution, stride 4);
+    ``noise`` is the amplitude of the uniform background noise (0 for smooth, up-sampled-looking maps).
     """
     rng = np.random.default_rng(seed)
     joints = sample_skeletons(rng, persons, H, W, edge=edge, scale_range=scale_range)
@@ -145,7 +147,7 @@ def make_image(seed: int, H: int = 128, W: int = 128, persons: int = 10, *,
         c = int(rng.choice([4, 7, 10, 13]))
         joints[p, c, 0] = rng.uniform(4, W - 5)
         joints[p, c, 1] = rng.uniform(4, H - 5)
-    heat, paf = render(joints, visible, H, W, rng, limbs=limbs, noise_levels=noise_levels, sigma_scale=sigma_scale)
+    heat, paf = render(joints, visible, H, W, rng, limbs=limbs, noise=noise, noise_levels=noise_levels, sigma_scale=sigma_scale)
     for _ in range(spikes):
         c, y, x = int(rng.integers(NUM_PARTS)), int(rng.integers(H)), int(rng.integers(W))
         heat[c, y, x] = max(heat[c, y, x], np.float32(rng.uniform(0.12, 0.6)))

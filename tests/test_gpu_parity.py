@@ -367,3 +367,44 @@ def test_random_parameters_and_dirt_against_the_checker(env):
         assert (r.status == 0).all(), what + f" status {r.status}"
         for i in range(3):
             _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), what + f" image {i}")
+
+
+@pytest.mark.parametrize("mode", ["f32", "f64", "f32-as-f64"])
+def test_512_planes_full_batch(env, mode):
+    """parity at 512x512 rested on 2 images.  32 images of smooth 512x512 maps (bodies and blobs 4x, as the
+    x4 bicubic up-sampling of predict() produces them), 14 persons each, all three body-part dtypes: the keypoint planes
+    take the band kernel, the body-part planes (1 / 2 MiB each) are sampled through L2."""
+    t = env.torch
+    N = 32
+    heat, paf = env.synth.make_batch(5120, N, 512, 512, 14, scale_range=(3.2, 5.2), sigma_scale=4.0, noise=0.0, drop_prob=0.05)
+    params = env.skeleton.default_params()
+    paf_ref = paf if mode == "f32" else paf.astype(np.float64)
+    o = env.so.group_batch(heat, paf_ref, env.skeleton.LIMBS, 512, params, threads=8)
+    g = env.Grouper(max_batch=N, max_h=512, max_w=512)
+    try:
+        hd = t.from_numpy(heat).to(env.dev)
+        pd = t.from_numpy(paf_ref if mode == "f64" else paf).to(env.dev)
+        g.group_device(hd, pd, 512, params, paf_as_f64=mode == "f32-as-f64")
+        r = g.fetch()
+        names = g.stage_kernels()
+    finally:
+        g.close()
+    assert (o.status == 0).all() and (r.status == 0).all() and r.n_persons.sum() > 10 * N
+    assert "false" in names[1], names
+    for i in range(N):
+        _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"{mode} image {i}")
+
+
+def test_f64_planes_full_batch(env):
+    """f64 parity rested on 8 images.  64 dirty 30-person images with float64 body-part maps whose values
+    are not float32-representable (what a multi-scale predict() returns)."""
+    t = env.torch
+    N = 64
+    heat, paf = env.synth.make_batch(6400, N, 128, 128, 30, drop_prob=0.08, spikes=6, colocate=1, edge=True)
+    paf64 = paf.astype(np.float64) * (1.0 + 2.0 ** -30) + 2.0 ** -40
+    params = env.skeleton.default_params()
+    o = env.so.group_batch(heat, paf64, env.skeleton.LIMBS, 128, params, threads=8)
+    r = _run_gpu(env, heat, paf64, 128, params)
+    assert (o.status == 0).all() and (r.status == 0).all()
+    for i in range(N):
+        _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")

@@ -4,7 +4,7 @@ set -u
 out=gpurun_out/r2_final
 mkdir -p $out
 python bench.py --steps 20 --warmup 5 > $out/bench_p30.json 2> $out/bench_p30.err
-for c in p10 f64 net128 512; do
+for c in p10 f64 net128 512 imhn; do
   python bench.py --config $c --steps 20 --warmup 5 > $out/bench_$c.json 2> $out/bench_$c.err
 done
 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_reference_arm.json 2> $out/bench_reference_arm.err
