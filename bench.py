@@ -335,10 +335,10 @@ def run_ours(args, rank, world, local_rank):
             if evs: evs[i].record(stream)
             if sink is not None and i == n_stage - 1:  # only the assemble stage needs the sink slot
                 g.set_wire_output(sink.begin(s, stream), 0, CAP_ROWS)
+                g.arm_wire_signal(sink.counter_address(s), s + 1)  # its last CTA publishes "step s landed" itself
             fn()
         if evs: evs[n_stage].record(stream)
         if sink is not None:
-            sink.publish(s, stream)
             if rank == 0:  # the consumer: waits for every rank's counters (stream memory ops), then frees the generation
                 sink.collect(s, cstream)
                 sink.release(s, cstream)

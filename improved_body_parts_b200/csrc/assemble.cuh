@@ -38,6 +38,11 @@ struct AssembleArgs {
     double len_rate, connection_tole, min_mean_score;
     int remove_recon, min_parts;
     int refresh_len_check;  // demo_image.py:414-415: the same-B refresh also checks the limb length
+    // "records landed" signal folded into the kernel (spg_arm_wire_signal): the CTA that finishes last release-stores
+    // wire_flag_value into *wire_flag (local or peer memory) -- no separate signalling kernel after the launch
+    unsigned long long *wire_flag;
+    unsigned long long wire_flag_value;
+    unsigned int *done_counter;
     Workspace ws;
 };
 
@@ -425,6 +430,18 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
         }
         double *rows = reinterpret_cast<double *>(rec + 8);
         for (int i = lane; i < wn * WR; i += 32) rows[i] = s_wire[i];
+    }
+    if (a.wire_flag != nullptr) {  // last CTA done publishes the step (the threadFenceReduction pattern, system scope)
+        __syncwarp();              // every lane's record stores are ordered before lane 0's fence
+        if (lane == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(a.done_counter, 1u);
+            if (prev == (unsigned int)a.n_images - 1u) {
+                *a.done_counter = 0u;  // re-armed for the next launch (stream order separates the launches)
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.wire_flag), "l"(a.wire_flag_value) : "memory");
+            }
+        }
     }
 }
 

@@ -43,6 +43,9 @@ struct spg_handle {
     // staging for spg_group_host
     void *in_heat = nullptr, *in_paf = nullptr;
     size_t in_heat_bytes = 0, in_paf_bytes = 0;
+    unsigned int *done_counter = nullptr;          // "last CTA done" counter of the in-kernel wire signal
+    unsigned long long *armed_flag = nullptr;      // spg_arm_wire_signal: consumed by the next assemble launch
+    unsigned long long armed_value = 0;
     double *heat_acc = nullptr;  // postnet: float64 accumulator of the keypoint maps over the scale loop
     size_t heat_acc_elems = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
@@ -247,6 +250,8 @@ int launch_assemble(spg_handle *h, int base, int n, const spg_params *p, cudaStr
     a.remove_recon = p->remove_recon;
     a.min_parts = p->min_parts;
     a.refresh_len_check = p->refresh_len_check != 0;
+    a.wire_flag = h->armed_flag; a.wire_flag_value = h->armed_value; a.done_counter = h->done_counter;
+    h->armed_flag = nullptr;  // one shot
     a.ws = h->ws;
     a.ws.wire_first += base;  // records are indexed by the image's position in the call
     a.use_bulk = ((size_t)h->ws.L * h->ws.capP * sizeof(uint32_t)) % 16 == 0;  // bulk copies move multiples of 16 bytes
@@ -271,6 +276,7 @@ int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, c
     a.remove_recon = p->remove_recon;
     a.min_parts = p->min_parts;
     a.refresh_len_check = p->refresh_len_check != 0;
+    a.wire_flag = h->armed_flag; a.wire_flag_value = h->armed_value; a.done_counter = h->done_counter;
     a.ws = h->ws;
     a.ws.wire_first += base;
     a.use_bulk = 0;
@@ -278,8 +284,9 @@ int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, c
     if (smem > h->smem_optin) {  // very large capacities: the two stand-alone kernels need less shared memory
         int rc;
         if ((rc = launch_match(h, base, n, st))) return rc;
-        return launch_assemble(h, base, n, p, st);
+        return launch_assemble(h, base, n, p, st);  // consumes the armed signal itself
     }
+    h->armed_flag = nullptr;  // one shot
     SPG_CUDA(h, cudaFuncSetAttribute(match_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_assemble_kernel<<<n, kMAThreads, smem, st>>>(a, h->cand_dtype == SPG_F32);
     h->stage_kernel[2] = "match_assemble_kernel";
@@ -422,6 +429,7 @@ void spg_destroy(spg_handle *h) {
     if (h->in_heat) cudaFree(h->in_heat);
     if (h->in_paf) cudaFree(h->in_paf);
     if (h->heat_acc) cudaFree(h->heat_acc);
+    if (h->done_counter) cudaFree(h->done_counter);
     for (auto &s : h->streams)
         if (s) cudaStreamDestroy(s);
     delete h;
@@ -464,6 +472,23 @@ int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int
     h->ws.wire = static_cast<unsigned char *>(wire_dev);
     h->ws.wire_first = first_record;
     h->ws.wire_rows = wire_rows;
+    return SPG_OK;
+}
+
+int spg_arm_wire_signal(spg_handle *h, uint64_t *word_dev, uint64_t value) {
+    if (!h) return SPG_E_INVALID;
+    if (!word_dev) {
+        h->armed_flag = nullptr;
+        return SPG_OK;
+    }
+    if (!h->ws.wire) return fail(h, SPG_E_STATE, "spg_arm_wire_signal needs a wire output (spg_set_wire_output) first");
+    if (!h->done_counter) {
+        DeviceGuard guard(h->device);
+        SPG_CUDA(h, cudaMalloc(&h->done_counter, sizeof(unsigned int)));
+        SPG_CUDA(h, cudaMemset(h->done_counter, 0, sizeof(unsigned int)));
+    }
+    h->armed_flag = reinterpret_cast<unsigned long long *>(word_dev);
+    h->armed_value = value;
     return SPG_OK;
 }
 
@@ -576,6 +601,7 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
         const size_t need = (size_t)h->cfg.max_batch * ws.K * H * W;
         if (h->heat_acc_elems < need) {
             if (h->heat_acc) cudaFree(h->heat_acc);
+    if (h->done_counter) cudaFree(h->done_counter);
             h->heat_acc = nullptr; h->heat_acc_elems = 0;
             SPG_CUDA(h, cudaMalloc(&h->heat_acc, need * sizeof(double)));
             h->heat_acc_elems = need;

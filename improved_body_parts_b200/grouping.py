@@ -30,7 +30,7 @@ EXPORTS = (
     "spg_assemble", "spg_upload_peaks", "spg_upload_connections", "spg_download_peaks", "spg_download_connections",
     "spg_download_people", "spg_download_status", "spg_launch_count", "spg_stage_kernel", "spg_wire_record_bytes",
     "spg_set_wire_output", "spg_wire_create", "spg_wire_open", "spg_wire_close", "spg_wire_destroy", "spg_wire_signal",
-    "spg_wire_wait", "spg_postnet", "spg_match_assemble", "spg_wire_signal_many")
+    "spg_wire_wait", "spg_postnet", "spg_match_assemble", "spg_wire_signal_many", "spg_arm_wire_signal")
 
 
 class GroupingError(RuntimeError):
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
         lib.spg_wire_record_bytes.restype = C.c_int64
         lib.spg_wire_record_bytes.argtypes = [C.c_void_p]
         lib.spg_set_wire_output.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        lib.spg_arm_wire_signal.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.spg_wire_create.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
         lib.spg_wire_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
         lib.spg_wire_close.argtypes = [C.c_void_p]
@@ -319,6 +320,12 @@ class Grouper:
         rc = self._lib.spg_set_wire_output(self._h, C.c_void_p(dev_ptr or 0), C.c_int64(first_record),
                                            C.c_int32(self.capR if rows is None else rows))
         self._check(rc, "spg_set_wire_output")
+
+    def arm_wire_signal(self, word_ptr: Optional[int], value: int = 0) -> None:
+        """The next single-launch assemble stage release-stores ``value`` into the 64-bit word at ``word_ptr`` (local or
+        peer memory) when its last CTA is done: the "records landed" signal without a separate kernel.  One shot."""
+        rc = self._lib.spg_arm_wire_signal(self._h, C.c_void_p(word_ptr or 0), C.c_uint64(value))
+        self._check(rc, "spg_arm_wire_signal")
 
     # -- helpers ---------------------------------------------------------------------------------
     def _stream_ptr(self, stream) -> C.c_void_p:

@@ -164,8 +164,14 @@ class PeerWireSink:
             self.G.wire_wait(self.device, self._mail_local, step - self.slots + 1, stream)
         return self._sink + self.HEADER + (step % self.slots) * self.gen_bytes + self.offset * self.record_bytes
 
+    def counter_address(self, step: int) -> int:
+        """Address (in ``dst``'s memory) of this rank's "landed" counter for ``step``; the value to store is ``step + 1``."""
+        return self._sink + ((step % self.slots) * self.world + self.rank) * 8
+
     def publish(self, step: int, stream) -> None:
-        self.G.wire_signal(self.device, self._sink + ((step % self.slots) * self.world + self.rank) * 8, step + 1, stream)
+        """Signal with a separate one-thread kernel.  ``Grouper.arm_wire_signal(sink.counter_address(s), s + 1)`` before
+        the assemble launch does the same from inside the kernel and needs no launch."""
+        self.G.wire_signal(self.device, self.counter_address(step), step + 1, stream)
 
     # -- consumer side (dst) ----------------------------------------------------------------------------
     def collect(self, step: int, stream):

@@ -220,6 +220,12 @@ int64_t spg_wire_record_bytes(const spg_handle *h);
  * wire_rows <= max_person_rows caps the rows per record (SPG_ST_WIRE_OVERFLOW).  NULL switches wire output off. */
 int spg_set_wire_output(spg_handle *h, void *wire_dev, int64_t first_record, int32_t wire_rows);
 
+/* Arm the NEXT single-launch assemble stage (spg_assemble / spg_match_assemble / spg_group_batch; not spg_group_host,
+ * which launches per chunk) to publish its own completion: the CTA that finishes last release-stores `value` into
+ * *word_dev (local or peer memory) after every record of the launch has been stored -- the producer's "my records
+ * have landed" without a separate signalling kernel.  One shot; NULL disarms.  Needs spg_set_wire_output. */
+int spg_arm_wire_signal(spg_handle *h, uint64_t *word_dev, uint64_t value);
+
 /* ---- peer memory + stream-ordered signalling for the NVLink gather (no NCCL in the data path) ------------ */
 /* A sink is plain device memory that other processes (one per GPU) can map: create it on the owner, send the
  * 64-byte handle to the peers by any means (torch.distributed), open it there.  Zero-filled on creation. */

@@ -178,6 +178,8 @@ def _peer_worker(rank, world, port, n_images, mode, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
+    armed = mode == "peer-armed"  # the assemble kernel's last CTA publishes the step itself (spg_arm_wire_signal)
+    mode = "peer" if armed else mode
     dist.init_process_group("nccl" if mode == "packed" else "gloo", rank=rank, world_size=world,
                             **({"device_id": dev} if mode == "packed" else {}))
     try:
@@ -198,11 +200,14 @@ def _peer_worker(rank, world, port, n_images, mode, q):
             hd, pd = torch.from_numpy(heat).to(dev), torch.from_numpy(paf).to(dev)
             if mode == "peer":
                 g.set_wire_output(sink.begin(s, stream), 0, ROWS)
+                if armed:
+                    g.arm_wire_signal(sink.counter_address(s), s + 1)
             else:
                 g.set_wire_output(pg.local.data_ptr(), 0, ROWS)
             g.group_device(hd, pd, 128, params)
             if mode == "peer":
-                sink.publish(s, stream)
+                if not armed:
+                    sink.publish(s, stream)
                 if rank == 0:
                     view = sink.collect(s, cstream)
                     with torch.cuda.stream(cstream):
@@ -225,7 +230,7 @@ def _peer_worker(rank, world, port, n_images, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,n", [("peer", 12), ("peer", 7), ("packed", 7)])
+@pytest.mark.parametrize("mode,n", [("peer", 12), ("peer", 7), ("peer-armed", 12), ("peer-armed", 5), ("packed", 7)])
 def test_two_gpu_gather_equals_one_gpu(env, mode, n):
     t = env.torch
     if t.cuda.device_count() < 2:
