@@ -68,6 +68,37 @@ def test_wire_records_are_the_process_tail(env):
     assert any(isinstance(x, int) for v in people.values() for pts, _ in v for x, _ in pts)
 
 
+def test_armed_signal_is_published_by_the_assemble_kernel(env):
+    """spg_arm_wire_signal: the last CTA of the next assemble launch release-stores the value (here into local memory);
+    one shot -- the following launch leaves the word alone; both the fused and the stand-alone kernel carry it."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(808, 9, 128, 128, 8)
+    params = env.skeleton.default_params()
+    g = env.Grouper(max_batch=9)
+    try:
+        hd, pd = t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev)
+        buf = t.zeros((9, g.wire_record_bytes()), dtype=t.uint8, device=env.dev)
+        word = t.zeros((2,), dtype=t.int64, device=env.dev)
+        g.set_wire_output(buf.data_ptr())
+        g.arm_wire_signal(word.data_ptr(), 41)
+        g.group_device(hd, pd, 128, params)            # fused match_assemble
+        t.cuda.synchronize()
+        assert word.tolist() == [41, 0]
+        g.group_device(hd, pd, 128, params)            # not armed any more
+        g.arm_wire_signal(word.data_ptr() + 8, 77)
+        g.assemble(9, params)                          # the stand-alone kernel
+        t.cuda.synchronize()
+        assert word.tolist() == [41, 77]
+        rec = env.wire.as_records(buf.cpu().numpy(), 17, g.capR)
+        assert (rec["n_persons"] > 0).all()
+        g.set_wire_output(None)
+        from improved_body_parts_b200.grouping import GroupingError
+        with pytest.raises(GroupingError, match="wire output"):
+            g.arm_wire_signal(word.data_ptr(), 1)
+    finally:
+        g.close()
+
+
 def test_wire_row_capacity_is_flagged_not_overrun(env):
     from improved_body_parts_b200.grouping import ST_WIRE_OVERFLOW
     heat, paf = env.synth.make_batch(77, 3, 96, 96, 6)
