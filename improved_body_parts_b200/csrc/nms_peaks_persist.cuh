@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
     uint32_t *s_lists = reinterpret_cast<uint32_t *>(smem_raw + kNmsPSlots * plane_stride);  // [lists][capP]
     uint16_t *s_queues = reinterpret_cast<uint16_t *>(s_lists + kNmsPLists * (size_t)capP);
     const int W4 = W >> 2, groups = H * W4;
+    // g / W4 without a division: groups < 2^16 here (launch condition), so umulhi(g, ceil(2^32 / W4)) is exact
+    const uint32_t w4_magic = W4 > 1 ? 0xffffffffu / (uint32_t)W4 + 1u : 0u;
     const int gpw = (groups + kNmsPScanners - 1) / kNmsPScanners;
 
     if (tid == 0) {
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
             // ---- pass 2: 8-neighbour test (neighbours clamped to the image == window clipped to the image)
             for (int q = lane; q < nq; q += 32) {
                 const int g = wq[q];
-                const int y = g / W4, xq = g - y * W4;
+                const int y = W4 > 1 ? (int)__umulhi((uint32_t)g, w4_magic) : g, xq = g - y * W4;
                 const int x0 = 4 * xq;
                 const float *rc = buf + (size_t)y * W;
                 const float *ru = buf + (size_t)max(y - 1, 0) * W;
