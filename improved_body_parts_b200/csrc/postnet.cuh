@@ -57,6 +57,7 @@ struct PostArgs {
     int scale_index, n_scales;  // accumulate over the scale loop (:160-161)
     int nan_scrub;              // demo_image.py:179-180: NaN -> 0 after the accumulation
     int tile_w, tile_h, tiles_x, tiles_y;
+    int chan_chunk;             // stride-4 kernel: channels one CTA walks over (grid.y = ceil(n_out / chan_chunk))
     double sx1, sy1, sx2, sy2;  // source step per destination pixel of the two resizes
 };
 
@@ -217,182 +218,194 @@ __global__ void __launch_bounds__(kPostThreads) postnet_generic_kernel(PostArgs 
 // (d + 0.5) / 4 - 0.5 = q + g_r for d = 4q + r, g_r in {-0.375, -0.125, 0.125, 0.375}: exact in float, so the weights of
 // destination index d depend on r alone and its taps are source indices q-2..q+1 (r < 2) or q-1..q+2 (r >= 2).  One
 // thread therefore loads FIVE source values and produces FOUR outputs (a float4 store), in both the horizontal and the
-// vertical pass; there are no per-element tables, no integer divisions and no clamps except on the five loads.  The
-// second resize stays table driven (general ratio) but tiles that touch no border read their four taps at
-// base, base+1, base+2, base+3.  Same operations in the same order as the generic kernel: identical maps.
+// vertical pass.  Everything that depends only on the tile POSITION -- the second resize's weights and tap offsets, the
+// clamped row / column offsets of all four passes -- is computed once per CTA, and the CTA then walks over a chunk of
+// CHANNELS of its tile (the first version rebuilt the tables for every (tile, channel) CTA: 40 % of its instructions
+// were table set-up, 36 % per-row index arithmetic).  Same operations in the same order as the generic kernel:
+// identical maps.
 constexpr int kPostF_C1 = 104, kPostF_R1 = 56;
-constexpr size_t kPostF_SmemBytes = (size_t)(kPostTW + kPostTH) * (sizeof(float4) + sizeof(int)) +
-                                    sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
-                                                     (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
+constexpr int kPostF_Q = kPostF_C1 / 4, kPostF_P = kPostF_R1 / 4;
+struct PostTabs {
+    float4 w2x[kPostTW], w2y[kPostTH];   // weights of the second resize per output column / row of the tile
+    int4 o2x[kPostTW], o2y[kPostTH];     // its four tap offsets: columns of s2 (elements), rows of s3 (elements, x kPostTW)
+    int o1x[kPostF_Q][5];                // pass 1: the five source columns of group q (elements of an s0 row)
+    int o1y[kPostF_P][5];                // pass 2: the five source rows of group p (elements of s1, x kPostF_C1)
+    float4 wph[4];                       // the four weight sets of the x4 resize
+    int rng[8];
+};
+constexpr size_t kPostF_SmemBytes = sizeof(PostTabs) + sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
+                                                                         (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
 
 __device__ __forceinline__ float tap4w(float a0, float a1, float a2, float a3, const float4 &c) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c.x), __fmul_rn(a1, c.y)), __fmul_rn(a2, c.z)), __fmul_rn(a3, c.w));
 }
 
-__global__ void __launch_bounds__(kPostThreads) postnet_kernel(PostArgs a) {
+__global__ void __launch_bounds__(kPostThreads, 4) postnet_kernel(PostArgs a) {
     extern __shared__ __align__(16) unsigned char post_smem[];
-    float4 *w2x = reinterpret_cast<float4 *>(post_smem);   // weights of the second resize per output column / row of the tile
-    float4 *w2y = w2x + kPostTW;
-    int *b2x = reinterpret_cast<int *>(w2y + kPostTH);     // first tap (absolute crop coordinate, unclamped)
-    int *b2y = b2x + kPostTW;
-    float *s0 = reinterpret_cast<float *>(b2y + kPostTH);  // source tile, flip-averaged            [RS][kPostCS]
-    float *s1 = s0 + kPostRS * kPostCS;                    // after the horizontal x4 pass          [RS][kPostF_C1]
-    float *s2 = s1 + kPostRS * kPostF_C1;                  // after the vertical x4 pass            [4P][kPostF_C1]
-    float *s3 = s2 + kPostF_R1 * kPostF_C1;                // after the second resize's h. pass     [4P][kPostTW]
-    __shared__ float4 wph[4];                              // the four weight sets of the x4 resize
-    __shared__ int rng[10];
+    PostTabs &T = *reinterpret_cast<PostTabs *>(post_smem);
+    float *s0 = reinterpret_cast<float *>(post_smem + sizeof(PostTabs));  // source tile, flip-averaged      [RS][kPostCS]
+    float *s1 = s0 + kPostRS * kPostCS;                                   // after the horizontal x4 pass    [RS][kPostF_C1]
+    float *s2 = s1 + kPostRS * kPostF_C1;                                 // after the vertical x4 pass      [4P][kPostF_C1]
+    float *s3 = s2 + kPostF_R1 * kPostF_C1;                               // after the 2nd resize's h. pass  [4P][kPostTW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, c = blockIdx.y, n = blockIdx.z;
+    constexpr int NW = kPostThreads / 32;
+    const int tile = blockIdx.x, n = blockIdx.z;
+    const int c_begin = blockIdx.y * a.chan_chunk, c_end = min(c_begin + a.chan_chunk, a.n_out);
     const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
     const int ox0 = tx * a.tile_w, oy0 = ty * a.tile_h;
     const int tw = min(a.tile_w, a.W - ox0), th = min(a.tile_h, a.H - oy0);
     const bool identity = a.crop_h == a.H && a.crop_w == a.W;  // second resize with scale 1: weights (0, 1, 0, 0)
 
+    // ---- once per CTA: everything that depends on the tile position only
     if (tid < tw) {
         float cc[4];
-        b2x[tid] = axis_entry(ox0 + tid, a.sx2, cc);
-        w2x[tid] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        T.o2x[tid].x = axis_entry(ox0 + tid, a.sx2, cc);  // first tap (absolute crop column, unclamped) for now
+        T.w2x[tid] = make_float4(cc[0], cc[1], cc[2], cc[3]);
     } else if (tid >= 64 && tid < 64 + th) {
         float cc[4];
-        b2y[tid - 64] = axis_entry(oy0 + tid - 64, a.sy2, cc);
-        w2y[tid - 64] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        T.o2y[tid - 64].x = axis_entry(oy0 + tid - 64, a.sy2, cc);
+        T.w2y[tid - 64] = make_float4(cc[0], cc[1], cc[2], cc[3]);
     } else if (tid >= 128 && tid < 132) {
         float cc[4];
         axis_entry(4 + (tid - 128), 0.25, cc);  // destination 4 + r: the same fraction as every 4q + r
-        wph[tid - 128] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        T.wph[tid - 128] = make_float4(cc[0], cc[1], cc[2], cc[3]);
     }
     __syncthreads();
     if (tid == 0) {
         // crop-coordinate range the tile reads (taps clamped to the cropped array, :148-149), widened to multiples of 4
-        const int c_lo = identity ? ox0 : clampi(b2x[0], 0, a.crop_w - 1), c_hi = identity ? ox0 + tw - 1 : clampi(b2x[tw - 1] + 3, 0, a.crop_w - 1);
-        const int y_lo = identity ? oy0 : clampi(b2y[0], 0, a.crop_h - 1), y_hi = identity ? oy0 + th - 1 : clampi(b2y[th - 1] + 3, 0, a.crop_h - 1);
+        const int c_lo = identity ? ox0 : clampi(T.o2x[0].x, 0, a.crop_w - 1), c_hi = identity ? ox0 + tw - 1 : clampi(T.o2x[tw - 1].x + 3, 0, a.crop_w - 1);
+        const int y_lo = identity ? oy0 : clampi(T.o2y[0].x, 0, a.crop_h - 1), y_hi = identity ? oy0 + th - 1 : clampi(T.o2y[th - 1].x + 3, 0, a.crop_h - 1);
         const int q_lo = c_lo >> 2, Q = (c_hi >> 2) - q_lo + 1, p_lo = y_lo >> 2, P = (y_hi >> 2) - p_lo + 1;
         const int sc_lo = max(q_lo - 2, 0), sc_hi = min(q_lo + Q + 1, a.w - 1);
         const int sr_lo = max(p_lo - 2, 0), sr_hi = min(p_lo + P + 1, a.h - 1);
-        rng[0] = q_lo; rng[1] = Q; rng[2] = p_lo; rng[3] = P;
-        rng[4] = sc_lo; rng[5] = sc_hi - sc_lo + 1; rng[6] = sr_lo; rng[7] = sr_hi - sr_lo + 1;
-        rng[8] = y_lo; rng[9] = y_hi;
+        T.rng[0] = q_lo; T.rng[1] = Q; T.rng[2] = p_lo; T.rng[3] = P;
+        T.rng[4] = sc_lo; T.rng[5] = sc_hi - sc_lo + 1; T.rng[6] = sr_lo; T.rng[7] = sr_hi - sr_lo + 1;
     }
     __syncthreads();
-    const int q_lo = rng[0], Q = rng[1], p_lo = rng[2], P = rng[3], sc_lo = rng[4], CS = rng[5], sr_lo = rng[6], RS = rng[7];
-    const int c_lo_a = 4 * q_lo, y_lo_a = 4 * p_lo, C1 = 4 * Q;
+    const int q_lo = T.rng[0], Q = T.rng[1], p_lo = T.rng[2], P = T.rng[3], sc_lo = T.rng[4], CS = T.rng[5], sr_lo = T.rng[6], RS = T.rng[7];
+    const int c_lo_a = 4 * q_lo, y_lo_a = 4 * p_lo, C1 = 4 * Q, R1 = 4 * P;
+    {   // tap offsets of the four passes, clamps applied here once
+        if (tid < tw) {
+            const int b = T.o2x[tid].x;
+            T.o2x[tid] = make_int4(clampi(b, 0, a.crop_w - 1) - c_lo_a, clampi(b + 1, 0, a.crop_w - 1) - c_lo_a,
+                                   clampi(b + 2, 0, a.crop_w - 1) - c_lo_a, clampi(b + 3, 0, a.crop_w - 1) - c_lo_a);
+        } else if (tid >= 64 && tid < 64 + th) {
+            const int b = T.o2y[tid - 64].x;
+            T.o2y[tid - 64] = make_int4((clampi(b, 0, a.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 1, 0, a.crop_h - 1) - y_lo_a) * kPostTW,
+                                        (clampi(b + 2, 0, a.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 3, 0, a.crop_h - 1) - y_lo_a) * kPostTW);
+        } else if (tid >= 128 && tid < 128 + Q) {
+            const int qa = q_lo + tid - 128;
+#pragma unroll
+            for (int k = 0; k < 5; k++) T.o1x[tid - 128][k] = clampi(qa - 2 + k, 0, a.w - 1) - sc_lo;
+        } else if (tid >= 192 && tid < 192 + P) {
+            const int pa = p_lo + tid - 192;
+#pragma unroll
+            for (int k = 0; k < 5; k++) T.o1y[tid - 192][k] = (clampi(pa - 2 + k, 0, a.h - 1) - sr_lo) * kPostF_C1;
+        }
+    }
+    __syncthreads();
+    const float4 W0 = T.wph[0], W1 = T.wph[1], W2 = T.wph[2], W3 = T.wph[3];
+    const float nf = (float)a.n_scales;
+    const size_t plane = (size_t)a.H * a.W;
+    const bool first = a.scale_index == 0, last = a.scale_index == a.n_scales - 1;
+    // rows of the intermediate the second resize reads: [y_lo, y_hi] relative to the aligned origin (identity: the tile's own rows)
+    const int yr_lo = identity ? 0 : T.o2y[0].x / kPostTW, yr_hi = identity ? R1 - 1 : T.o2y[th - 1].w / kPostTW;
 
-    // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
-    {
-        const long long base0 = (long long)n * a.img_stride + (long long)a.src_chan[c] * a.chan_stride;
-        const long long base1 = (long long)n * a.img_stride + a.pair_stride + (long long)a.flip_chan[c] * a.chan_stride;
-        for (int i = warp; i < RS; i += kPostThreads / 32) {
-            const long long r0 = base0 + (long long)(sr_lo + i) * a.w, r1 = base1 + (long long)(sr_lo + i) * a.w;
-            for (int j = lane; j < CS; j += 32) {
-                const int x = sc_lo + j;
-                float v0, v1;
-                if (a.net_is_f16) {
-                    const __half *p = static_cast<const __half *>(a.net);
-                    v0 = __half2float(p[r0 + x]);
-                    v1 = __half2float(p[r1 + (a.w - 1 - x)]);
-                } else {
-                    const float *p = static_cast<const float *>(a.net);
-                    v0 = p[r0 + x];
-                    v1 = p[r1 + (a.w - 1 - x)];
+    for (int c = c_begin; c < c_end; c++) {
+        // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
+        {
+            const long long base0 = (long long)n * a.img_stride + (long long)a.src_chan[c] * a.chan_stride + (long long)sr_lo * a.w;
+            const long long base1 = (long long)n * a.img_stride + a.pair_stride + (long long)a.flip_chan[c] * a.chan_stride + (long long)sr_lo * a.w;
+            for (int i = warp; i < RS; i += NW) {
+                const long long r0 = base0 + (long long)i * a.w + sc_lo, r1 = base1 + (long long)i * a.w + (a.w - 1 - sc_lo);
+                for (int j = lane; j < CS; j += 32) {
+                    float v0, v1;
+                    if (a.net_is_f16) {
+                        const __half *p = static_cast<const __half *>(a.net);
+                        v0 = __half2float(p[r0 + j]);
+                        v1 = __half2float(p[r1 - j]);
+                    } else {
+                        const float *p = static_cast<const float *>(a.net);
+                        v0 = p[r0 + j];
+                        v1 = p[r1 - j];
+                    }
+                    s0[i * kPostCS + j] = __fdiv_rn(__fadd_rn(v0, v1), 2.0f);
                 }
-                s0[i * kPostCS + j] = __fdiv_rn(__fadd_rn(v0, v1), 2.0f);
-            }
-        }
-    }
-    __syncthreads();
-    const float4 W0 = wph[0], W1 = wph[1], W2 = wph[2], W3 = wph[3];
-    // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
-    for (int i = warp; i < RS; i += kPostThreads / 32) {
-        const float *row = s0 + i * kPostCS - sc_lo;
-        for (int q = lane; q < Q; q += 32) {
-            const int qa = q_lo + q;
-            const float v0 = row[clampi(qa - 2, 0, a.w - 1)], v1 = row[clampi(qa - 1, 0, a.w - 1)], v2 = row[min(qa, a.w - 1)],
-                        v3 = row[min(qa + 1, a.w - 1)], v4 = row[min(qa + 2, a.w - 1)];
-            float4 o;
-            o.x = tap4w(v0, v1, v2, v3, W0);
-            o.y = tap4w(v0, v1, v2, v3, W1);
-            o.z = tap4w(v1, v2, v3, v4, W2);
-            o.w = tap4w(v1, v2, v3, v4, W3);
-            *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = o;
-        }
-    }
-    __syncthreads();
-    // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157)
-    for (int p = warp; p < P; p += kPostThreads / 32) {
-        const int pa = p_lo + p;
-        const int r0 = (clampi(pa - 2, 0, a.h - 1) - sr_lo) * kPostF_C1, r1 = (clampi(pa - 1, 0, a.h - 1) - sr_lo) * kPostF_C1,
-                  r2 = (min(pa, a.h - 1) - sr_lo) * kPostF_C1, r3 = (min(pa + 1, a.h - 1) - sr_lo) * kPostF_C1,
-                  r4 = (min(pa + 2, a.h - 1) - sr_lo) * kPostF_C1;
-        float *dst = s2 + 4 * p * kPostF_C1;
-        for (int X = lane; X < C1; X += 32) {
-            const float v0 = s1[r0 + X], v1 = s1[r1 + X], v2 = s1[r2 + X], v3 = s1[r3 + X], v4 = s1[r4 + X];
-            dst[X] = tap4w(v0, v1, v2, v3, W0);
-            dst[kPostF_C1 + X] = tap4w(v0, v1, v2, v3, W1);
-            dst[2 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W2);
-            dst[3 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W3);
-        }
-    }
-    __syncthreads();
-    // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs (taps clamped to the cropped array)
-    const int y_lo = rng[8], y_hi = rng[9];
-    if (!identity) {
-        const bool inner = b2x[0] >= 0 && b2x[tw - 1] + 3 <= a.crop_w - 1;  // no tap of this tile is clamped (block-uniform)
-        for (int Y = y_lo - y_lo_a + warp; Y <= y_hi - y_lo_a; Y += kPostThreads / 32) {
-            const float *row = s2 + Y * kPostF_C1 - c_lo_a;
-            for (int x = lane; x < tw; x += 32) {
-                const int b = b2x[x];
-                float a0, a1, a2, a3;
-                if (inner) {
-                    a0 = row[b]; a1 = row[b + 1]; a2 = row[b + 2]; a3 = row[b + 3];
-                } else {
-                    a0 = row[clampi(b, 0, a.crop_w - 1)]; a1 = row[clampi(b + 1, 0, a.crop_w - 1)];
-                    a2 = row[clampi(b + 2, 0, a.crop_w - 1)]; a3 = row[clampi(b + 3, 0, a.crop_w - 1)];
-                }
-                s3[Y * kPostTW + x] = tap4w(a0, a1, a2, a3, w2x[x]);
             }
         }
         __syncthreads();
-    }
-    // ---- pass 4 + epilogue: vertical pass, / n in float32, float64 accumulation over the scale loop (:160-161)
-    const float nf = (float)a.n_scales;
-    const size_t plane = (size_t)a.H * a.W;
-    const bool is_heat = c < a.K;
-    const size_t pbase = is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane;
-    const bool first = a.scale_index == 0, last = a.scale_index == a.n_scales - 1;
-    const bool inner_y = identity || (b2y[0] >= 0 && b2y[th - 1] + 3 <= a.crop_h - 1);
-    for (int y = warp; y < th; y += kPostThreads / 32) {
-        int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-        float4 wy = make_float4(0.f, 1.f, 0.f, 0.f);
+        // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
+        for (int i = warp; i < RS; i += NW) {
+            const float *row = s0 + i * kPostCS;
+            for (int q = lane; q < Q; q += 32) {
+                const int *o = T.o1x[q];
+                const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
+                float4 r;
+                r.x = tap4w(v0, v1, v2, v3, W0);
+                r.y = tap4w(v0, v1, v2, v3, W1);
+                r.z = tap4w(v1, v2, v3, v4, W2);
+                r.w = tap4w(v1, v2, v3, v4, W3);
+                *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = r;
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157)
+        for (int p = warp; p < P; p += NW) {
+            const int *o = T.o1y[p];
+            const int r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3], r4 = o[4];
+            float *dst = s2 + 4 * p * kPostF_C1;
+            for (int X = lane; X < C1; X += 32) {
+                const float v0 = s1[r0 + X], v1 = s1[r1 + X], v2 = s1[r2 + X], v3 = s1[r3 + X], v4 = s1[r4 + X];
+                dst[X] = tap4w(v0, v1, v2, v3, W0);
+                dst[kPostF_C1 + X] = tap4w(v0, v1, v2, v3, W1);
+                dst[2 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W2);
+                dst[3 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W3);
+            }
+        }
+        __syncthreads();
+        // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs
         if (!identity) {
-            const int b = b2y[y];
-            wy = w2y[y];
-            if (inner_y) {
-                o0 = (b - y_lo_a) * kPostTW; o1 = o0 + kPostTW; o2 = o1 + kPostTW; o3 = o2 + kPostTW;
-            } else {
-                o0 = (clampi(b, 0, a.crop_h - 1) - y_lo_a) * kPostTW; o1 = (clampi(b + 1, 0, a.crop_h - 1) - y_lo_a) * kPostTW;
-                o2 = (clampi(b + 2, 0, a.crop_h - 1) - y_lo_a) * kPostTW; o3 = (clampi(b + 3, 0, a.crop_h - 1) - y_lo_a) * kPostTW;
+            for (int Y = yr_lo + warp; Y <= yr_hi; Y += NW) {
+                const float *row = s2 + Y * kPostF_C1;
+                for (int x = lane; x < tw; x += 32) {
+                    const int4 o = T.o2x[x];
+                    s3[Y * kPostTW + x] = tap4w(row[o.x], row[o.y], row[o.z], row[o.w], T.w2x[x]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- pass 4 + epilogue: vertical pass, / n in float32, float64 accumulation over the scale loop (:160-161)
+        const bool is_heat = c < a.K;
+        const size_t pbase = (is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane) + (size_t)oy0 * a.W + ox0;
+        for (int y = warp; y < th; y += NW) {
+            int4 o = make_int4(0, 0, 0, 0);
+            float4 wy = make_float4(0.f, 1.f, 0.f, 0.f);
+            if (!identity) {
+                o = T.o2y[y];
+                wy = T.w2y[y];
+            }
+            const size_t orow = pbase + (size_t)y * a.W;
+            const float *idrow = s2 + (oy0 + y - y_lo_a) * kPostF_C1 + (ox0 - c_lo_a);
+            for (int x = lane; x < tw; x += 32) {
+                const float v = identity ? idrow[x] : tap4w(s3[o.x + x], s3[o.y + x], s3[o.z + x], s3[o.w + x], wy);
+                const size_t oo = orow + x;
+                const float part = a.n_scales == 1 ? v : __fdiv_rn(v, nf);  // float32 array / Python int -> float32 (x / 1 == x)
+                if (a.n_scales == 1) {  // avg = 0.0 + part: exact, the float64 value is the float32 one
+                    const float r = (a.nan_scrub && part != part) ? 0.0f : part;
+                    if (is_heat) a.heat[oo] = r;
+                    else if (a.paf_is_f64) static_cast<double *>(a.paf)[oo] = (double)r;
+                    else static_cast<float *>(a.paf)[oo] = r;
+                } else {
+                    double *acc = is_heat ? a.heat_acc : static_cast<double *>(a.paf);
+                    double sacc = __dadd_rn(first ? 0.0 : acc[oo], (double)part);
+                    if (a.nan_scrub && sacc != sacc) sacc = 0.0;  // demo_image.py:179-180 scrubs after every scale
+                    acc[oo] = sacc;
+                    if (is_heat && last) a.heat[oo] = (float)sacc;  // find_peaks: heatmap_avg.astype(np.float32)
+                }
             }
         }
-        const size_t orow = pbase + (size_t)(oy0 + y) * a.W + ox0;
-        for (int x = lane; x < tw; x += 32) {
-            const float v = identity ? s2[(oy0 + y - y_lo_a) * kPostF_C1 + (ox0 + x - c_lo_a)]
-                                     : tap4w(s3[o0 + x], s3[o1 + x], s3[o2 + x], s3[o3 + x], wy);
-            const size_t o = orow + x;
-            const float part = a.n_scales == 1 ? v : __fdiv_rn(v, nf);  // float32 array / Python int -> float32 (x / 1 == x)
-            if (a.n_scales == 1) {  // avg = 0.0 + part: exact, the float64 value is the float32 one
-                const float r = (a.nan_scrub && part != part) ? 0.0f : part;
-                if (is_heat) a.heat[o] = r;
-                else if (a.paf_is_f64) static_cast<double *>(a.paf)[o] = (double)r;
-                else static_cast<float *>(a.paf)[o] = r;
-            } else {
-                double *acc = is_heat ? a.heat_acc : static_cast<double *>(a.paf);
-                double s = __dadd_rn(first ? 0.0 : acc[o], (double)part);
-                if (a.nan_scrub && s != s) s = 0.0;  // demo_image.py:179-180 scrubs after every scale
-                acc[o] = s;
-                if (is_heat && last) a.heat[o] = (float)s;  // find_peaks: heatmap_avg.astype(np.float32)
-            }
-        }
+        __syncthreads();  // s0..s3 are reused by the next channel
     }
 }
 

@@ -645,7 +645,12 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
         a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
         a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
         if ((long long)a.tiles_x * a.tiles_y > 0x7fffffffLL || n > 65535) return fail(h, SPG_E_INVALID, "postnet grid too large");
-        dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)a.n_out, (unsigned)n);
+        // stride-4 kernel: a CTA builds its tile's tables once and walks over a chunk of channels -- as many as still leave
+        // ~16 CTAs per SM in the grid (4 resident: several waves)
+        const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
+        const int n_chunks = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 16 + tiles - 1) / tiles));
+        a.chan_chunk = fast ? (a.n_out + n_chunks - 1) / n_chunks : 1;
+        dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
         if (fast) {
             SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostF_SmemBytes));
             postnet_kernel<<<grid, kPostThreads, kPostF_SmemBytes, st>>>(a);
