@@ -38,13 +38,25 @@ constexpr int kPostC1 = 96, kPostR1 = 48;     // capacity of the intermediate (c
 constexpr int kPostCS = 32, kPostRS = 20;     // capacity of the source tile (network resolution)
 constexpr int kMaxNetChannels = 64;
 
-struct PostArgs {
+constexpr int kPostMaxScales = 4;  // scales the stride-4 kernel fuses into one launch (more: one launch per group of 4)
+struct PostScale {              // one entry of the scale loop (evaluate.py:90)
     const void *net;            // [N][2][C][h][w]: image, mirrored image (evaluate.py:116-126)
     int net_is_f16;             // 0: float32, 1: float16 (converted on load)
     long long img_stride, pair_stride, chan_stride;  // elements
     int h, w;                   // network output size
-    int stride;                 // model_params['stride']
     int crop_h, crop_w;         // imageToTest size = padded size minus pad[2], pad[3] (pad[0] = pad[1] = 0 always)
+    double sx2, sy2;            // source step per destination pixel of the resize to the image
+};
+
+struct PostArgs {
+    const void *net;            // (generic kernel: the one scale of this launch; the stride-4 kernel reads `sc`)
+    int net_is_f16;
+    long long img_stride, pair_stride, chan_stride;
+    int h, w;
+    int stride;                 // model_params['stride']
+    int crop_h, crop_w;
+    PostScale sc[kPostMaxScales];  // stride-4 kernel: the scales summed inside ONE launch, in the order of the scale loop
+    int n_fused;                // entries of `sc` in this launch; scale_index is the index of sc[0] in the whole loop
     int H, W;                   // image size = output size
     int n_out;                  // output channels handled: K keypoint + L body-part
     int K;                      // first K outputs are keypoint channels
@@ -219,10 +231,13 @@ __global__ void __launch_bounds__(kPostThreads) postnet_generic_kernel(PostArgs 
 // destination index d depend on r alone and its taps are source indices q-2..q+1 (r < 2) or q-1..q+2 (r >= 2).  One
 // thread therefore loads FIVE source values and produces FOUR outputs (a float4 store), in both the horizontal and the
 // vertical pass.  Everything that depends only on the tile POSITION -- the second resize's weights and tap offsets, the
-// clamped row / column offsets of all four passes -- is computed once per CTA, and the CTA then walks over a chunk of
-// CHANNELS of its tile (the first version rebuilt the tables for every (tile, channel) CTA: 40 % of its instructions
-// were table set-up, 36 % per-row index arithmetic).  Same operations in the same order as the generic kernel:
-// identical maps.
+// clamped row / column offsets of all four passes -- is computed once per CTA (per scale), and the CTA then walks over a
+// chunk of CHANNELS of its tile (the first version rebuilt the tables for every (tile, channel) CTA: 40 % of its
+// instructions were table set-up, 36 % per-row index arithmetic).
+// The SCALE LOOP of predict() (:90, :160-161) runs inside the kernel: a thread keeps the float64 sums of its output
+// pixels in registers while it works through the scales, so the averaged maps are written exactly once -- a launch per
+// scale would read-modify-write 48 float64 planes per extra scale (3.6x the traffic at 3 scales).
+// Same operations in the same order as the generic kernel: identical maps.
 constexpr int kPostF_C1 = 104, kPostF_R1 = 56;
 constexpr int kPostF_Q = kPostF_C1 / 4, kPostF_P = kPostF_R1 / 4;
 struct PostTabs {
@@ -233,179 +248,235 @@ struct PostTabs {
     float4 wph[4];                       // the four weight sets of the x4 resize
     int rng[8];
 };
-constexpr size_t kPostF_SmemBytes = sizeof(PostTabs) + sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
-                                                                         (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
+constexpr size_t kPostF_SmemBytes = kPostMaxScales * sizeof(PostTabs) +
+                                    sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
+                                                     (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
 
 __device__ __forceinline__ float tap4w(float a0, float a1, float a2, float a3, const float4 &c) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c.x), __fmul_rn(a1, c.y)), __fmul_rn(a2, c.z)), __fmul_rn(a3, c.w));
 }
 
-__global__ void __launch_bounds__(kPostThreads, 4) postnet_kernel(PostArgs a) {
+__global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
     extern __shared__ __align__(16) unsigned char post_smem[];
-    PostTabs &T = *reinterpret_cast<PostTabs *>(post_smem);
-    float *s0 = reinterpret_cast<float *>(post_smem + sizeof(PostTabs));  // source tile, flip-averaged      [RS][kPostCS]
+    PostTabs *TT = reinterpret_cast<PostTabs *>(post_smem);
+    float *s0 = reinterpret_cast<float *>(post_smem + kPostMaxScales * sizeof(PostTabs));  // source tile, flip-averaged [RS][kPostCS]
     float *s1 = s0 + kPostRS * kPostCS;                                   // after the horizontal x4 pass    [RS][kPostF_C1]
     float *s2 = s1 + kPostRS * kPostF_C1;                                 // after the vertical x4 pass      [4P][kPostF_C1]
     float *s3 = s2 + kPostF_R1 * kPostF_C1;                               // after the 2nd resize's h. pass  [4P][kPostTW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kPostThreads / 32;
+    constexpr int KY = kPostTH / NW, KX = kPostTW / 32;  // output pixels per thread: rows warp + NW * ky, columns lane + 32 * kx
     const int tile = blockIdx.x, n = blockIdx.z;
     const int c_begin = blockIdx.y * a.chan_chunk, c_end = min(c_begin + a.chan_chunk, a.n_out);
     const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
     const int ox0 = tx * a.tile_w, oy0 = ty * a.tile_h;
     const int tw = min(a.tile_w, a.W - ox0), th = min(a.tile_h, a.H - oy0);
-    const bool identity = a.crop_h == a.H && a.crop_w == a.W;  // second resize with scale 1: weights (0, 1, 0, 0)
 
-    // ---- once per CTA: everything that depends on the tile position only
-    if (tid < tw) {
-        float cc[4];
-        T.o2x[tid].x = axis_entry(ox0 + tid, a.sx2, cc);  // first tap (absolute crop column, unclamped) for now
-        T.w2x[tid] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-    } else if (tid >= 64 && tid < 64 + th) {
-        float cc[4];
-        T.o2y[tid - 64].x = axis_entry(oy0 + tid - 64, a.sy2, cc);
-        T.w2y[tid - 64] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-    } else if (tid >= 128 && tid < 132) {
-        float cc[4];
-        axis_entry(4 + (tid - 128), 0.25, cc);  // destination 4 + r: the same fraction as every 4q + r
-        T.wph[tid - 128] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        // crop-coordinate range the tile reads (taps clamped to the cropped array, :148-149), widened to multiples of 4
-        const int c_lo = identity ? ox0 : clampi(T.o2x[0].x, 0, a.crop_w - 1), c_hi = identity ? ox0 + tw - 1 : clampi(T.o2x[tw - 1].x + 3, 0, a.crop_w - 1);
-        const int y_lo = identity ? oy0 : clampi(T.o2y[0].x, 0, a.crop_h - 1), y_hi = identity ? oy0 + th - 1 : clampi(T.o2y[th - 1].x + 3, 0, a.crop_h - 1);
-        const int q_lo = c_lo >> 2, Q = (c_hi >> 2) - q_lo + 1, p_lo = y_lo >> 2, P = (y_hi >> 2) - p_lo + 1;
-        const int sc_lo = max(q_lo - 2, 0), sc_hi = min(q_lo + Q + 1, a.w - 1);
-        const int sr_lo = max(p_lo - 2, 0), sr_hi = min(p_lo + P + 1, a.h - 1);
-        T.rng[0] = q_lo; T.rng[1] = Q; T.rng[2] = p_lo; T.rng[3] = P;
-        T.rng[4] = sc_lo; T.rng[5] = sc_hi - sc_lo + 1; T.rng[6] = sr_lo; T.rng[7] = sr_hi - sr_lo + 1;
-    }
-    __syncthreads();
-    const int q_lo = T.rng[0], Q = T.rng[1], p_lo = T.rng[2], P = T.rng[3], sc_lo = T.rng[4], CS = T.rng[5], sr_lo = T.rng[6], RS = T.rng[7];
-    const int c_lo_a = 4 * q_lo, y_lo_a = 4 * p_lo, C1 = 4 * Q, R1 = 4 * P;
-    {   // tap offsets of the four passes, clamps applied here once
+    // ---- once per CTA and scale: everything that depends on the tile position only
+    for (int t = 0; t < a.n_fused; t++) {
+        PostTabs &T = TT[t];
+        const PostScale &S = a.sc[t];
+        const bool identity = S.crop_h == a.H && S.crop_w == a.W;  // second resize with scale 1: weights (0, 1, 0, 0)
         if (tid < tw) {
-            const int b = T.o2x[tid].x;
-            T.o2x[tid] = make_int4(clampi(b, 0, a.crop_w - 1) - c_lo_a, clampi(b + 1, 0, a.crop_w - 1) - c_lo_a,
-                                   clampi(b + 2, 0, a.crop_w - 1) - c_lo_a, clampi(b + 3, 0, a.crop_w - 1) - c_lo_a);
+            float cc[4];
+            T.o2x[tid].x = axis_entry(ox0 + tid, S.sx2, cc);  // first tap (absolute crop column, unclamped) for now
+            T.w2x[tid] = make_float4(cc[0], cc[1], cc[2], cc[3]);
         } else if (tid >= 64 && tid < 64 + th) {
-            const int b = T.o2y[tid - 64].x;
-            T.o2y[tid - 64] = make_int4((clampi(b, 0, a.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 1, 0, a.crop_h - 1) - y_lo_a) * kPostTW,
-                                        (clampi(b + 2, 0, a.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 3, 0, a.crop_h - 1) - y_lo_a) * kPostTW);
-        } else if (tid >= 128 && tid < 128 + Q) {
-            const int qa = q_lo + tid - 128;
-#pragma unroll
-            for (int k = 0; k < 5; k++) T.o1x[tid - 128][k] = clampi(qa - 2 + k, 0, a.w - 1) - sc_lo;
-        } else if (tid >= 192 && tid < 192 + P) {
-            const int pa = p_lo + tid - 192;
-#pragma unroll
-            for (int k = 0; k < 5; k++) T.o1y[tid - 192][k] = (clampi(pa - 2 + k, 0, a.h - 1) - sr_lo) * kPostF_C1;
+            float cc[4];
+            T.o2y[tid - 64].x = axis_entry(oy0 + tid - 64, S.sy2, cc);
+            T.w2y[tid - 64] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        } else if (tid >= 128 && tid < 132) {
+            float cc[4];
+            axis_entry(4 + (tid - 128), 0.25, cc);  // destination 4 + r: the same fraction as every 4q + r
+            T.wph[tid - 128] = make_float4(cc[0], cc[1], cc[2], cc[3]);
         }
+        __syncthreads();
+        if (tid == 0) {
+            // crop-coordinate range the tile reads (taps clamped to the cropped array, :148-149), widened to multiples of 4
+            const int c_lo = identity ? ox0 : clampi(T.o2x[0].x, 0, S.crop_w - 1), c_hi = identity ? ox0 + tw - 1 : clampi(T.o2x[tw - 1].x + 3, 0, S.crop_w - 1);
+            const int y_lo = identity ? oy0 : clampi(T.o2y[0].x, 0, S.crop_h - 1), y_hi = identity ? oy0 + th - 1 : clampi(T.o2y[th - 1].x + 3, 0, S.crop_h - 1);
+            const int q_lo = c_lo >> 2, Q = (c_hi >> 2) - q_lo + 1, p_lo = y_lo >> 2, P = (y_hi >> 2) - p_lo + 1;
+            const int sc_lo = max(q_lo - 2, 0), sc_hi = min(q_lo + Q + 1, S.w - 1);
+            const int sr_lo = max(p_lo - 2, 0), sr_hi = min(p_lo + P + 1, S.h - 1);
+            T.rng[0] = q_lo; T.rng[1] = Q; T.rng[2] = p_lo; T.rng[3] = P;
+            T.rng[4] = sc_lo; T.rng[5] = sc_hi - sc_lo + 1; T.rng[6] = sr_lo; T.rng[7] = sr_hi - sr_lo + 1;
+        }
+        __syncthreads();
+        {   // tap offsets of the four passes, clamps applied here once
+            const int q_lo = T.rng[0], Q = T.rng[1], p_lo = T.rng[2], P = T.rng[3], sc_lo = T.rng[4], sr_lo = T.rng[6];
+            const int c_lo_a = 4 * q_lo, y_lo_a = 4 * p_lo;
+            if (tid < tw) {
+                const int b = T.o2x[tid].x;
+                T.o2x[tid] = make_int4(clampi(b, 0, S.crop_w - 1) - c_lo_a, clampi(b + 1, 0, S.crop_w - 1) - c_lo_a,
+                                       clampi(b + 2, 0, S.crop_w - 1) - c_lo_a, clampi(b + 3, 0, S.crop_w - 1) - c_lo_a);
+            } else if (tid >= 64 && tid < 64 + th) {
+                const int b = T.o2y[tid - 64].x;
+                T.o2y[tid - 64] = make_int4((clampi(b, 0, S.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 1, 0, S.crop_h - 1) - y_lo_a) * kPostTW,
+                                            (clampi(b + 2, 0, S.crop_h - 1) - y_lo_a) * kPostTW, (clampi(b + 3, 0, S.crop_h - 1) - y_lo_a) * kPostTW);
+            } else if (tid >= 128 && tid < 128 + Q) {
+                const int qa = q_lo + tid - 128;
+#pragma unroll
+                for (int k = 0; k < 5; k++) T.o1x[tid - 128][k] = clampi(qa - 2 + k, 0, S.w - 1) - sc_lo;
+            } else if (tid >= 192 && tid < 192 + P) {
+                const int pa = p_lo + tid - 192;
+#pragma unroll
+                for (int k = 0; k < 5; k++) T.o1y[tid - 192][k] = (clampi(pa - 2 + k, 0, S.h - 1) - sr_lo) * kPostF_C1;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const float4 W0 = T.wph[0], W1 = T.wph[1], W2 = T.wph[2], W3 = T.wph[3];
     const float nf = (float)a.n_scales;
     const size_t plane = (size_t)a.H * a.W;
-    const bool first = a.scale_index == 0, last = a.scale_index == a.n_scales - 1;
-    // rows of the intermediate the second resize reads: [y_lo, y_hi] relative to the aligned origin (identity: the tile's own rows)
-    const int yr_lo = identity ? 0 : T.o2y[0].x / kPostTW, yr_hi = identity ? R1 - 1 : T.o2y[th - 1].w / kPostTW;
+    const bool more_follow = a.scale_index + a.n_fused < a.n_scales;  // only with more than kPostMaxScales scales
 
-    for (int c = c_begin; c < c_end; c++) {
-        // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
-        {
-            const long long base0 = (long long)n * a.img_stride + (long long)a.src_chan[c] * a.chan_stride + (long long)sr_lo * a.w;
-            const long long base1 = (long long)n * a.img_stride + a.pair_stride + (long long)a.flip_chan[c] * a.chan_stride + (long long)sr_lo * a.w;
-            for (int i = warp; i < RS; i += NW) {
-                const long long r0 = base0 + (long long)i * a.w + sc_lo, r1 = base1 + (long long)i * a.w + (a.w - 1 - sc_lo);
-                for (int j = lane; j < CS; j += 32) {
-                    float v0, v1;
-                    if (a.net_is_f16) {
-                        const __half *p = static_cast<const __half *>(a.net);
-                        v0 = __half2float(p[r0 + j]);
-                        v1 = __half2float(p[r1 - j]);
-                    } else {
-                        const float *p = static_cast<const float *>(a.net);
-                        v0 = p[r0 + j];
-                        v1 = p[r1 - j];
-                    }
-                    s0[i * kPostCS + j] = __fdiv_rn(__fadd_rn(v0, v1), 2.0f);
+    constexpr int KI = (kPostRS + NW - 1) / NW;  // source rows per warp; a source tile row (<= 32 columns) is one lane each
+    float pv0[KI], pv1[KI];
+    auto prefetch = [&](int c, int t) {
+        const PostScale &S = a.sc[t];
+        const int sc_lo = TT[t].rng[4], CS = TT[t].rng[5], sr_lo = TT[t].rng[6], RS = TT[t].rng[7];
+        const long long base0 = (long long)n * S.img_stride + (long long)a.src_chan[c] * S.chan_stride + (long long)sr_lo * S.w + sc_lo;
+        const long long base1 = (long long)n * S.img_stride + S.pair_stride + (long long)a.flip_chan[c] * S.chan_stride + (long long)sr_lo * S.w + (S.w - 1 - sc_lo);
+#pragma unroll
+        for (int ki = 0; ki < KI; ki++) {
+            const int i = warp + NW * ki;
+            if (i < RS && lane < CS) {
+                if (S.net_is_f16) {
+                    const __half *p = static_cast<const __half *>(S.net);
+                    pv0[ki] = __half2float(p[base0 + (long long)i * S.w + lane]);
+                    pv1[ki] = __half2float(p[base1 + (long long)i * S.w - lane]);
+                } else {
+                    const float *p = static_cast<const float *>(S.net);
+                    pv0[ki] = p[base0 + (long long)i * S.w + lane];
+                    pv1[ki] = p[base1 + (long long)i * S.w - lane];
                 }
             }
         }
-        __syncthreads();
-        // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
-        for (int i = warp; i < RS; i += NW) {
-            const float *row = s0 + i * kPostCS;
-            for (int q = lane; q < Q; q += 32) {
-                const int *o = T.o1x[q];
-                const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
-                float4 r;
-                r.x = tap4w(v0, v1, v2, v3, W0);
-                r.y = tap4w(v0, v1, v2, v3, W1);
-                r.z = tap4w(v1, v2, v3, v4, W2);
-                r.w = tap4w(v1, v2, v3, v4, W3);
-                *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = r;
-            }
+    };
+    if (c_begin < c_end) prefetch(c_begin, 0);
+
+    for (int c = c_begin; c < c_end; c++) {
+        const bool is_heat = c < a.K;
+        const size_t pbase = (is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane) + (size_t)oy0 * a.W + ox0;
+        double acc[KY][KX];
+        if (a.scale_index > 0) {  // continuing a scale loop longer than one launch: the float64 sums so far
+            const double *prev = is_heat ? a.heat_acc : static_cast<const double *>(a.paf);
+#pragma unroll
+            for (int ky = 0; ky < KY; ky++)
+#pragma unroll
+                for (int kx = 0; kx < KX; kx++) {
+                    const int y = warp + NW * ky, x = lane + 32 * kx;
+                    acc[ky][kx] = (y < th && x < tw) ? prev[pbase + (size_t)y * a.W + x] : 0.0;
+                }
         }
-        __syncthreads();
-        // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157)
-        for (int p = warp; p < P; p += NW) {
-            const int *o = T.o1y[p];
-            const int r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3], r4 = o[4];
-            float *dst = s2 + 4 * p * kPostF_C1;
-            for (int X = lane; X < C1; X += 32) {
-                const float v0 = s1[r0 + X], v1 = s1[r1 + X], v2 = s1[r2 + X], v3 = s1[r3 + X], v4 = s1[r4 + X];
-                dst[X] = tap4w(v0, v1, v2, v3, W0);
-                dst[kPostF_C1 + X] = tap4w(v0, v1, v2, v3, W1);
-                dst[2 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W2);
-                dst[3 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W3);
+        for (int t = 0; t < a.n_fused; t++) {
+            const PostTabs &T = TT[t];
+            const PostScale &S = a.sc[t];
+            const bool identity = S.crop_h == a.H && S.crop_w == a.W;
+            const int q_lo = T.rng[0], Q = T.rng[1], p_lo = T.rng[2], P = T.rng[3], sc_lo = T.rng[4], CS = T.rng[5], sr_lo = T.rng[6], RS = T.rng[7];
+            const int c_lo_a = 4 * q_lo, y_lo_a = 4 * p_lo, C1 = 4 * Q, R1 = 4 * P;
+            const float4 W0 = T.wph[0], W1 = T.wph[1], W2 = T.wph[2], W3 = T.wph[3];
+            // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32.  Its global loads were
+            // issued one iteration ago (the chain load -> barrier -> four short passes is latency bound otherwise);
+            // commit them, then put the next iteration's loads in flight under this iteration's passes.
+#pragma unroll
+            for (int ki = 0; ki < KI; ki++) {
+                const int i = warp + NW * ki;
+                if (i < RS && lane < CS) s0[i * kPostCS + lane] = __fdiv_rn(__fadd_rn(pv0[ki], pv1[ki]), 2.0f);
             }
-        }
-        __syncthreads();
-        // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs
-        if (!identity) {
-            for (int Y = yr_lo + warp; Y <= yr_hi; Y += NW) {
-                const float *row = s2 + Y * kPostF_C1;
-                for (int x = lane; x < tw; x += 32) {
-                    const int4 o = T.o2x[x];
-                    s3[Y * kPostTW + x] = tap4w(row[o.x], row[o.y], row[o.z], row[o.w], T.w2x[x]);
+            __syncthreads();
+            {
+                int tn = t + 1, cn = c;
+                if (tn == a.n_fused) { tn = 0; cn = c + 1; }
+                if (cn < c_end) prefetch(cn, tn);
+            }
+            // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
+            for (int i = warp; i < RS; i += NW) {
+                const float *row = s0 + i * kPostCS;
+                for (int q = lane; q < Q; q += 32) {
+                    const int *o = T.o1x[q];
+                    const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
+                    float4 r;
+                    r.x = tap4w(v0, v1, v2, v3, W0);
+                    r.y = tap4w(v0, v1, v2, v3, W1);
+                    r.z = tap4w(v1, v2, v3, v4, W2);
+                    r.w = tap4w(v1, v2, v3, v4, W3);
+                    *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = r;
                 }
             }
             __syncthreads();
-        }
-        // ---- pass 4 + epilogue: vertical pass, / n in float32, float64 accumulation over the scale loop (:160-161)
-        const bool is_heat = c < a.K;
-        const size_t pbase = (is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane) + (size_t)oy0 * a.W + ox0;
-        for (int y = warp; y < th; y += NW) {
-            int4 o = make_int4(0, 0, 0, 0);
-            float4 wy = make_float4(0.f, 1.f, 0.f, 0.f);
-            if (!identity) {
-                o = T.o2y[y];
-                wy = T.w2y[y];
+            // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157)
+            for (int p = warp; p < P; p += NW) {
+                const int *o = T.o1y[p];
+                const int r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3], r4 = o[4];
+                float *dst = s2 + 4 * p * kPostF_C1;
+                for (int X = lane; X < C1; X += 32) {
+                    const float v0 = s1[r0 + X], v1 = s1[r1 + X], v2 = s1[r2 + X], v3 = s1[r3 + X], v4 = s1[r4 + X];
+                    dst[X] = tap4w(v0, v1, v2, v3, W0);
+                    dst[kPostF_C1 + X] = tap4w(v0, v1, v2, v3, W1);
+                    dst[2 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W2);
+                    dst[3 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W3);
+                }
             }
-            const size_t orow = pbase + (size_t)y * a.W;
-            const float *idrow = s2 + (oy0 + y - y_lo_a) * kPostF_C1 + (ox0 - c_lo_a);
-            for (int x = lane; x < tw; x += 32) {
-                const float v = identity ? idrow[x] : tap4w(s3[o.x + x], s3[o.y + x], s3[o.z + x], s3[o.w + x], wy);
-                const size_t oo = orow + x;
-                const float part = a.n_scales == 1 ? v : __fdiv_rn(v, nf);  // float32 array / Python int -> float32 (x / 1 == x)
-                if (a.n_scales == 1) {  // avg = 0.0 + part: exact, the float64 value is the float32 one
-                    const float r = (a.nan_scrub && part != part) ? 0.0f : part;
-                    if (is_heat) a.heat[oo] = r;
-                    else if (a.paf_is_f64) static_cast<double *>(a.paf)[oo] = (double)r;
-                    else static_cast<float *>(a.paf)[oo] = r;
-                } else {
-                    double *acc = is_heat ? a.heat_acc : static_cast<double *>(a.paf);
-                    double sacc = __dadd_rn(first ? 0.0 : acc[oo], (double)part);
-                    if (a.nan_scrub && sacc != sacc) sacc = 0.0;  // demo_image.py:179-180 scrubs after every scale
-                    acc[oo] = sacc;
-                    if (is_heat && last) a.heat[oo] = (float)sacc;  // find_peaks: heatmap_avg.astype(np.float32)
+            __syncthreads();
+            // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs
+            if (!identity) {
+                const int yr_lo = T.o2y[0].x / kPostTW, yr_hi = T.o2y[th - 1].w / kPostTW;
+                for (int Y = yr_lo + warp; Y <= yr_hi; Y += NW) {
+                    const float *row = s2 + Y * kPostF_C1;
+                    for (int x = lane; x < tw; x += 32) {
+                        const int4 o = T.o2x[x];
+                        s3[Y * kPostTW + x] = tap4w(row[o.x], row[o.y], row[o.z], row[o.w], T.w2x[x]);
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- pass 4: vertical pass, / n in float32, float64 sum over the scale loop (:160-161) in registers
+            const bool zero_start = a.scale_index == 0 && t == 0;
+#pragma unroll
+            for (int ky = 0; ky < KY; ky++) {
+                const int y = warp + NW * ky;
+                if (y < th) {
+                    int4 o = make_int4(0, 0, 0, 0);
+                    float4 wy = make_float4(0.f, 1.f, 0.f, 0.f);
+                    if (!identity) {
+                        o = T.o2y[y];
+                        wy = T.w2y[y];
+                    }
+                    const float *idrow = s2 + (oy0 + y - y_lo_a) * kPostF_C1 + (ox0 - c_lo_a);
+#pragma unroll
+                    for (int kx = 0; kx < KX; kx++) {
+                        const int x = lane + 32 * kx;
+                        if (x < tw) {
+                            const float v = identity ? idrow[x] : tap4w(s3[o.x + x], s3[o.y + x], s3[o.z + x], s3[o.w + x], wy);
+                            const float part = a.n_scales == 1 ? v : __fdiv_rn(v, nf);  // float32 array / Python int -> float32 (x / 1 == x)
+                            double sacc = __dadd_rn(zero_start ? 0.0 : acc[ky][kx], (double)part);
+                            if (a.nan_scrub && sacc != sacc) sacc = 0.0;  // demo_image.py:179-180 scrubs after every scale
+                            acc[ky][kx] = sacc;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // s0..s3 are reused by the next scale / channel
+        }
+        // ---- the averaged maps, written once: keypoint maps as float32 (find_peaks' cast, :173), body parts float64 / float32
+#pragma unroll
+        for (int ky = 0; ky < KY; ky++) {
+            const int y = warp + NW * ky;
+#pragma unroll
+            for (int kx = 0; kx < KX; kx++) {
+                const int x = lane + 32 * kx;
+                if (y < th && x < tw) {
+                    const size_t oo = pbase + (size_t)y * a.W + x;
+                    const double v = acc[ky][kx];
+                    if (is_heat) {
+                        if (more_follow) a.heat_acc[oo] = v;
+                        else a.heat[oo] = (float)v;
+                    } else if (a.paf_is_f64) static_cast<double *>(a.paf)[oo] = v;
+                    else static_cast<float *>(a.paf)[oo] = (float)v;
                 }
             }
         }
-        __syncthreads();  // s0..s3 are reused by the next channel
     }
 }
 

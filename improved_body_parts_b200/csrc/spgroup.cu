@@ -597,7 +597,7 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
     if (ws.K + ws.L > kMaxNetChannels) return fail(h, SPG_E_INVALID, "too many channels for postnet");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->n_scales > 1) {
+    if (d->n_scales > 1 && (d->stride != 4 || d->n_scales > kPostMaxScales)) {  // float64 keypoint sums that outlive a launch
         const size_t need = (size_t)h->cfg.max_batch * ws.K * H * W;
         if (h->heat_acc_elems < need) {
             if (h->heat_acc) cudaFree(h->heat_acc);
@@ -607,56 +607,85 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
             h->heat_acc_elems = need;
         }
     }
+    // validate every scale and fill the common arguments
+    PostArgs a{};
+    a.stride = d->stride; a.H = H; a.W = W; a.n_out = ws.K + ws.L; a.K = ws.K;
+    for (int c = 0; c < ws.K; c++) {
+        if (d->flip_heat_ord[c] < 0 || d->flip_heat_ord[c] >= ws.K) return fail(h, SPG_E_INVALID, "flip_heat_ord[%d] out of range", c);
+        a.src_chan[c] = (short)(d->heat_chan0 + c);
+        a.flip_chan[c] = (short)(d->heat_chan0 + d->flip_heat_ord[c]);
+    }
+    for (int k = 0; k < ws.L; k++) {
+        if (d->flip_paf_ord[k] < 0 || d->flip_paf_ord[k] >= ws.L) return fail(h, SPG_E_INVALID, "flip_paf_ord[%d] out of range", k);
+        a.src_chan[ws.K + k] = (short)(d->paf_chan0 + k);
+        a.flip_chan[ws.K + k] = (short)(d->paf_chan0 + d->flip_paf_ord[k]);
+    }
+    a.heat = heat_out; a.paf = paf_out; a.heat_acc = h->heat_acc; a.paf_is_f64 = paf_dtype == SPG_F64;
+    a.n_scales = d->n_scales; a.nan_scrub = d->nan_scrub != 0;
+    a.sx1 = 1.0 / (double)d->stride; a.sy1 = a.sx1;  // cv2.resize(fx = stride): scale = 1/fx
     for (int t = 0; t < d->n_scales; t++) {
         const spg_postnet_scale &sc = d->scales[t];
         if (!sc.net_out) return fail(h, SPG_E_INVALID, "scale %d: net_out is NULL", t);
         if (sc.dtype != SPG_F32 && sc.dtype != SPG_F16) return fail(h, SPG_E_INVALID, "scale %d: network output must be SPG_F32 or SPG_F16", t);
         if (sc.h < 1 || sc.w < 1 || sc.crop_h < 1 || sc.crop_w < 1 || sc.crop_h > sc.h * d->stride || sc.crop_w > sc.w * d->stride)
             return fail(h, SPG_E_INVALID, "scale %d: crop %dx%d does not fit the up-sampled %dx%d output", t, sc.crop_h, sc.crop_w, sc.h * d->stride, sc.w * d->stride);
-        PostArgs a{};
-        a.net = sc.net_out; a.net_is_f16 = sc.dtype == SPG_F16;
-        a.img_stride = sc.image_stride; a.pair_stride = sc.pair_stride; a.chan_stride = sc.chan_stride;
-        a.h = sc.h; a.w = sc.w; a.stride = d->stride; a.crop_h = sc.crop_h; a.crop_w = sc.crop_w;
-        a.H = H; a.W = W; a.n_out = ws.K + ws.L; a.K = ws.K;
-        for (int c = 0; c < ws.K; c++) {
-            if (d->flip_heat_ord[c] < 0 || d->flip_heat_ord[c] >= ws.K) return fail(h, SPG_E_INVALID, "flip_heat_ord[%d] out of range", c);
-            a.src_chan[c] = (short)(d->heat_chan0 + c);
-            a.flip_chan[c] = (short)(d->heat_chan0 + d->flip_heat_ord[c]);
+    }
+    auto scale_of = [&](const spg_postnet_scale &sc) {
+        PostScale s{};
+        s.net = sc.net_out; s.net_is_f16 = sc.dtype == SPG_F16;
+        s.img_stride = sc.image_stride; s.pair_stride = sc.pair_stride; s.chan_stride = sc.chan_stride;
+        s.h = sc.h; s.w = sc.w; s.crop_h = sc.crop_h; s.crop_w = sc.crop_w;
+        // cv2.resize(dsize): inv_scale = dst/src, scale = 1/inv_scale (two roundings, as OpenCV)
+        s.sx2 = 1.0 / ((double)W / (double)sc.crop_w);
+        s.sy2 = 1.0 / ((double)H / (double)sc.crop_h);
+        return s;
+    };
+    // output tile: as large as the shared-memory tiles of the intermediate / source allow
+    auto tile_dim = [&](double s2, double s1, int cap1, int cap0, int maxd, double margin) {
+        const double c1 = std::min((double)cap1, ((double)cap0 - 7.0) / s1) - margin;  // intermediate span allowed
+        return std::max(1, std::min(maxd, (int)(c1 / std::max(s2, 1e-6))));
+    };
+    const bool fast = d->stride == 4;  // the reference's model: four-phase kernel; other strides: table-driven generic kernel
+    if (fast) {
+        // the scale loop runs INSIDE the kernel (groups of kPostMaxScales): one tile geometry for all fused scales
+        for (int t0 = 0; t0 < d->n_scales; t0 += kPostMaxScales) {
+            a.n_fused = std::min(kPostMaxScales, d->n_scales - t0);
+            a.scale_index = t0;
+            a.tile_w = kPostTW; a.tile_h = kPostTH;
+            for (int t = 0; t < a.n_fused; t++) {
+                a.sc[t] = scale_of(d->scales[t0 + t]);
+                a.tile_w = std::min(a.tile_w, tile_dim(a.sc[t].sx2, a.sx1, kPostF_C1, kPostCS, kPostTW, 13.0));
+                a.tile_h = std::min(a.tile_h, tile_dim(a.sc[t].sy2, a.sy1, kPostF_R1, kPostRS, kPostTH, 13.0));
+            }
+            a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
+            a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
+            if ((long long)a.tiles_x * a.tiles_y > 0x7fffffffLL || n > 65535) return fail(h, SPG_E_INVALID, "postnet grid too large");
+            // a CTA builds its tile's tables once and walks over a chunk of channels -- as many as still leave
+            // ~16 CTAs per SM in the grid (3 resident: several waves)
+            const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
+            const int n_chunks = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 16 + tiles - 1) / tiles));
+            a.chan_chunk = (a.n_out + n_chunks - 1) / n_chunks;
+            dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
+            SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostF_SmemBytes));
+            postnet_kernel<<<grid, kPostThreads, kPostF_SmemBytes, st>>>(a);
+            h->launches++;
+            SPG_CUDA(h, cudaGetLastError());
         }
-        for (int k = 0; k < ws.L; k++) {
-            if (d->flip_paf_ord[k] < 0 || d->flip_paf_ord[k] >= ws.L) return fail(h, SPG_E_INVALID, "flip_paf_ord[%d] out of range", k);
-            a.src_chan[ws.K + k] = (short)(d->paf_chan0 + k);
-            a.flip_chan[ws.K + k] = (short)(d->paf_chan0 + d->flip_paf_ord[k]);
-        }
-        a.heat = heat_out; a.paf = paf_out; a.heat_acc = h->heat_acc; a.paf_is_f64 = paf_dtype == SPG_F64;
-        a.scale_index = t; a.n_scales = d->n_scales; a.nan_scrub = d->nan_scrub != 0;
-        // cv2.resize(fx = stride): scale = 1/fx;  cv2.resize(dsize): inv_scale = dst/src, scale = 1/inv_scale (two roundings, as OpenCV)
-        a.sx1 = 1.0 / (double)d->stride; a.sy1 = a.sx1;
-        a.sx2 = 1.0 / ((double)W / (double)sc.crop_w);
-        a.sy2 = 1.0 / ((double)H / (double)sc.crop_h);
-        // output tile: as large as the shared-memory tiles of the intermediate / source allow
-        const bool fast = d->stride == 4;  // the reference's model: four-phase kernel; other strides: table-driven generic kernel
-        auto tile_dim = [&](double s2, double s1, int cap1, int cap0, int maxd, double margin) {
-            const double c1 = std::min((double)cap1, ((double)cap0 - 7.0) / s1) - margin;  // intermediate span allowed
-            return std::max(1, std::min(maxd, (int)(c1 / std::max(s2, 1e-6))));
-        };
-        a.tile_w = fast ? tile_dim(a.sx2, a.sx1, kPostF_C1, kPostCS, kPostTW, 13.0) : tile_dim(a.sx2, a.sx1, kPostC1, kPostCS, kPostTW, 7.0);
-        a.tile_h = fast ? tile_dim(a.sy2, a.sy1, kPostF_R1, kPostRS, kPostTH, 13.0) : tile_dim(a.sy2, a.sy1, kPostR1, kPostRS, kPostTH, 7.0);
+        return SPG_OK;
+    }
+    for (int t = 0; t < d->n_scales; t++) {  // generic kernel: one launch per scale, float64 accumulators in memory
+        const PostScale s = scale_of(d->scales[t]);
+        a.net = s.net; a.net_is_f16 = s.net_is_f16; a.img_stride = s.img_stride; a.pair_stride = s.pair_stride; a.chan_stride = s.chan_stride;
+        a.h = s.h; a.w = s.w; a.crop_h = s.crop_h; a.crop_w = s.crop_w; a.sx2 = s.sx2; a.sy2 = s.sy2;
+        a.scale_index = t;
+        a.tile_w = tile_dim(a.sx2, a.sx1, kPostC1, kPostCS, kPostTW, 7.0);
+        a.tile_h = tile_dim(a.sy2, a.sy1, kPostR1, kPostRS, kPostTH, 7.0);
         a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
         a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
         if ((long long)a.tiles_x * a.tiles_y > 0x7fffffffLL || n > 65535) return fail(h, SPG_E_INVALID, "postnet grid too large");
-        // stride-4 kernel: a CTA builds its tile's tables once and walks over a chunk of channels -- as many as still leave
-        // ~16 CTAs per SM in the grid (4 resident: several waves)
-        const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
-        const int n_chunks = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 16 + tiles - 1) / tiles));
-        a.chan_chunk = fast ? (a.n_out + n_chunks - 1) / n_chunks : 1;
-        dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
-        if (fast) {
-            SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostF_SmemBytes));
-            postnet_kernel<<<grid, kPostThreads, kPostF_SmemBytes, st>>>(a);
-        } else {
-            postnet_generic_kernel<<<grid, kPostThreads, 0, st>>>(a);
-        }
+        a.chan_chunk = 1;
+        dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)a.n_out, (unsigned)n);
+        postnet_generic_kernel<<<grid, kPostThreads, 0, st>>>(a);
         h->launches++;
         SPG_CUDA(h, cudaGetLastError());
     }

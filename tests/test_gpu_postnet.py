@@ -72,6 +72,8 @@ CASES = {
     "many_tiles_ratio_1.33": ([(48, 64)], [(192, 250)], (144, 188)),       # several tiles per axis, inner and border ones
     "ratio_2_and_0.5": ([(64, 32)], [(256, 128)], (128, 256)),             # crop twice / half the image
     "tiny": ([(3, 5)], [(9, 17)], (7, 23)),
+    # more scales than one launch fuses (4): the float64 sums continue through memory in the second launch
+    "five_scales": ([(8, 8), (12, 12), (16, 16), (24, 24), (32, 32)], [(30, 30), (48, 48), (64, 64), (90, 90), (128, 128)], (64, 64)),
 }
 
 
