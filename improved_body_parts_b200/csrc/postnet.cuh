@@ -248,18 +248,22 @@ struct PostTabs {
     float4 wph[4];                       // the four weight sets of the x4 resize
     int rng[8];
 };
-constexpr size_t kPostF_SmemBytes = kPostMaxScales * sizeof(PostTabs) +
-                                    sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
-                                                     (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
+constexpr size_t postF_smem_bytes(int n_tabs) {
+    return n_tabs * sizeof(PostTabs) + sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
+                                                        (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
+}
 
 __device__ __forceinline__ float tap4w(float a0, float a1, float a2, float a3, const float4 &c) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c.x), __fmul_rn(a1, c.y)), __fmul_rn(a2, c.z)), __fmul_rn(a3, c.w));
 }
 
-__global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
+// SINGLE: one scale in the whole loop (the reference's default): no float64 sums, the maps are stored from pass 4.
+template <bool SINGLE>
+__global__ void __launch_bounds__(kPostThreads, SINGLE ? 4 : 3) postnet_kernel(PostArgs a) {
+    constexpr int kTabs = SINGLE ? 1 : kPostMaxScales;
     extern __shared__ __align__(16) unsigned char post_smem[];
     PostTabs *TT = reinterpret_cast<PostTabs *>(post_smem);
-    float *s0 = reinterpret_cast<float *>(post_smem + kPostMaxScales * sizeof(PostTabs));  // source tile, flip-averaged [RS][kPostCS]
+    float *s0 = reinterpret_cast<float *>(post_smem + kTabs * sizeof(PostTabs));  // source tile, flip-averaged [RS][kPostCS]
     float *s1 = s0 + kPostRS * kPostCS;                                   // after the horizontal x4 pass    [RS][kPostF_C1]
     float *s2 = s1 + kPostRS * kPostF_C1;                                 // after the vertical x4 pass      [4P][kPostF_C1]
     float *s3 = s2 + kPostF_R1 * kPostF_C1;                               // after the 2nd resize's h. pass  [4P][kPostTW]
@@ -358,15 +362,19 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
     for (int c = c_begin; c < c_end; c++) {
         const bool is_heat = c < a.K;
         const size_t pbase = (is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane) + (size_t)oy0 * a.W + ox0;
-        double acc[KY][KX];
-        if (a.scale_index > 0) {  // continuing a scale loop longer than one launch: the float64 sums so far
+        // output rows of this thread (32-bit offsets from one base pointer per channel; the dtype branches are block-uniform)
+        float *const out_f = is_heat ? a.heat + pbase : static_cast<float *>(a.paf) + pbase;
+        double *const out_d = (is_heat ? a.heat_acc : static_cast<double *>(a.paf)) + (is_heat && a.heat_acc == nullptr ? 0 : pbase);
+        const bool store_f = is_heat ? !more_follow : !a.paf_is_f64;
+        double acc[SINGLE ? 1 : KY][SINGLE ? 1 : KX];
+        if (!SINGLE && a.scale_index > 0) {  // continuing a scale loop longer than one launch: the float64 sums so far
             const double *prev = is_heat ? a.heat_acc : static_cast<const double *>(a.paf);
 #pragma unroll
             for (int ky = 0; ky < KY; ky++)
 #pragma unroll
                 for (int kx = 0; kx < KX; kx++) {
                     const int y = warp + NW * ky, x = lane + 32 * kx;
-                    acc[ky][kx] = (y < th && x < tw) ? prev[pbase + (size_t)y * a.W + x] : 0.0;
+                    acc[SINGLE ? 0 : ky][SINGLE ? 0 : kx] = (y < th && x < tw) ? prev[pbase + (size_t)y * a.W + x] : 0.0;
                 }
         }
         for (int t = 0; t < a.n_fused; t++) {
@@ -444,15 +452,22 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
                         wy = T.w2y[y];
                     }
                     const float *idrow = s2 + (oy0 + y - y_lo_a) * kPostF_C1 + (ox0 - c_lo_a);
+                    const int orow = y * a.W;
 #pragma unroll
                     for (int kx = 0; kx < KX; kx++) {
                         const int x = lane + 32 * kx;
                         if (x < tw) {
                             const float v = identity ? idrow[x] : tap4w(s3[o.x + x], s3[o.y + x], s3[o.z + x], s3[o.w + x], wy);
-                            const float part = a.n_scales == 1 ? v : __fdiv_rn(v, nf);  // float32 array / Python int -> float32 (x / 1 == x)
-                            double sacc = __dadd_rn(zero_start ? 0.0 : acc[ky][kx], (double)part);
-                            if (a.nan_scrub && sacc != sacc) sacc = 0.0;  // demo_image.py:179-180 scrubs after every scale
-                            acc[ky][kx] = sacc;
+                            if (SINGLE) {  // avg = 0.0 + v / 1: the float64 value is this float32 one
+                                const float r = (a.nan_scrub && v != v) ? 0.0f : v;  // demo_image.py:179-180
+                                if (store_f) out_f[orow + x] = r;
+                                else out_d[orow + x] = (double)r;
+                            } else {
+                                const float part = __fdiv_rn(v, nf);  // float32 array / Python int -> float32
+                                double sacc = __dadd_rn(zero_start ? 0.0 : acc[SINGLE ? 0 : ky][SINGLE ? 0 : kx], (double)part);
+                                if (a.nan_scrub && sacc != sacc) sacc = 0.0;  // demo_image.py:179-180 scrubs after every scale
+                                acc[SINGLE ? 0 : ky][SINGLE ? 0 : kx] = sacc;
+                            }
                         }
                     }
                 }
@@ -460,20 +475,19 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
             __syncthreads();  // s0..s3 are reused by the next scale / channel
         }
         // ---- the averaged maps, written once: keypoint maps as float32 (find_peaks' cast, :173), body parts float64 / float32
+        if (!SINGLE) {
 #pragma unroll
-        for (int ky = 0; ky < KY; ky++) {
-            const int y = warp + NW * ky;
+            for (int ky = 0; ky < KY; ky++) {
+                const int y = warp + NW * ky;
+                const int orow = y * a.W;
 #pragma unroll
-            for (int kx = 0; kx < KX; kx++) {
-                const int x = lane + 32 * kx;
-                if (y < th && x < tw) {
-                    const size_t oo = pbase + (size_t)y * a.W + x;
-                    const double v = acc[ky][kx];
-                    if (is_heat) {
-                        if (more_follow) a.heat_acc[oo] = v;
-                        else a.heat[oo] = (float)v;
-                    } else if (a.paf_is_f64) static_cast<double *>(a.paf)[oo] = v;
-                    else static_cast<float *>(a.paf)[oo] = (float)v;
+                for (int kx = 0; kx < KX; kx++) {
+                    const int x = lane + 32 * kx;
+                    if (y < th && x < tw) {
+                        const double v = acc[SINGLE ? 0 : ky][SINGLE ? 0 : kx];
+                        if (store_f) out_f[orow + x] = (float)v;
+                        else out_d[orow + x] = v;
+                    }
                 }
             }
         }

@@ -666,8 +666,13 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
             const int n_chunks = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 16 + tiles - 1) / tiles));
             a.chan_chunk = (a.n_out + n_chunks - 1) / n_chunks;
             dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
-            SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPostF_SmemBytes));
-            postnet_kernel<<<grid, kPostThreads, kPostF_SmemBytes, st>>>(a);
+            if (d->n_scales == 1) {
+                SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)postF_smem_bytes(1)));
+                postnet_kernel<true><<<grid, kPostThreads, postF_smem_bytes(1), st>>>(a);
+            } else {
+                SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)postF_smem_bytes(kPostMaxScales)));
+                postnet_kernel<false><<<grid, kPostThreads, postF_smem_bytes(kPostMaxScales), st>>>(a);
+            }
             h->launches++;
             SPG_CUDA(h, cudaGetLastError());
         }
