@@ -666,13 +666,28 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
             const int n_chunks = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 16 + tiles - 1) / tiles));
             a.chan_chunk = (a.n_out + n_chunks - 1) / n_chunks;
             dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
-            if (d->n_scales == 1) {
-                SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)postF_smem_bytes(1)));
-                postnet_kernel<true><<<grid, kPostThreads, postF_smem_bytes(1), st>>>(a);
-            } else {
-                SPG_CUDA(h, cudaFuncSetAttribute(postnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)postF_smem_bytes(kPostMaxScales)));
-                postnet_kernel<false><<<grid, kPostThreads, postF_smem_bytes(kPostMaxScales), st>>>(a);
+            bool ident = true, any16 = false, all16 = true;
+            for (int t = 0; t < a.n_fused; t++) {
+                ident = ident && a.sc[t].crop_h == H && a.sc[t].crop_w == W;
+                any16 = any16 || a.sc[t].net_is_f16;
+                all16 = all16 && a.sc[t].net_is_f16;
             }
+            if (any16 != all16) return fail(h, SPG_E_INVALID, "the network outputs of all scales must have the same dtype");
+            const bool single = d->n_scales == 1;
+            const size_t smem = postF_smem_bytes(single ? 1 : kPostMaxScales);
+#define SPG_POST_LAUNCH(S_, I_, F_)                                                                                           \
+    do {                                                                                                                      \
+        SPG_CUDA(h, (cudaFuncSetAttribute(postnet_kernel<S_, I_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))); \
+        postnet_kernel<S_, I_, F_><<<grid, kPostThreads, smem, st>>>(a);                                                      \
+    } while (0)
+            if (single) {
+                if (ident) { if (all16) SPG_POST_LAUNCH(true, true, true); else SPG_POST_LAUNCH(true, true, false); }
+                else { if (all16) SPG_POST_LAUNCH(true, false, true); else SPG_POST_LAUNCH(true, false, false); }
+            } else {
+                if (ident) { if (all16) SPG_POST_LAUNCH(false, true, true); else SPG_POST_LAUNCH(false, true, false); }
+                else { if (all16) SPG_POST_LAUNCH(false, false, true); else SPG_POST_LAUNCH(false, false, false); }
+            }
+#undef SPG_POST_LAUNCH
             h->launches++;
             SPG_CUDA(h, cudaGetLastError());
         }
