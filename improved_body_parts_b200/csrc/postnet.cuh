@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
             }
             // ---- pass 4: vertical pass, / n in float32, float64 sum over the scale loop (:160-161) in registers
             const bool zero_start = a.scale_index == 0 && t == 0;
+            float r1[SINGLE ? KY : 1][SINGLE ? KX : 1];  // single scale: the values this thread stores
 #pragma unroll
             for (int ky = 0; ky < KY; ky++) {
                 const int y = warp + NW * ky;
@@ -454,7 +455,6 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
                         wy = T.w2y[y];
                     }
                     const float *idrow = s2 + (oy0 + y - y_lo_a) * kPostF_C1 + (ox0 - c_lo_a);
-                    const int orow = y * a.W;
 #pragma unroll
                     for (int kx = 0; kx < KX; kx++) {
                         const int x = lane + 32 * kx;
@@ -463,9 +463,7 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
                             if (IDENT) v = idrow[x];
                             else v = identity ? idrow[x] : tap4w(s3[o.x + x], s3[o.y + x], s3[o.z + x], s3[o.w + x], wy);
                             if (SINGLE) {  // avg = 0.0 + v / 1: the float64 value is this float32 one
-                                const float r = (a.nan_scrub && v != v) ? 0.0f : v;  // demo_image.py:179-180
-                                if (store_f) out_f[orow + x] = r;
-                                else out_d[orow + x] = (double)r;
+                                r1[SINGLE ? ky : 0][SINGLE ? kx : 0] = (a.nan_scrub && v != v) ? 0.0f : v;  // demo_image.py:179-180
                             } else {
                                 const float part = __fdiv_rn(v, nf);  // float32 array / Python int -> float32
                                 double sacc = __dadd_rn(zero_start ? 0.0 : acc[SINGLE ? 0 : ky][SINGLE ? 0 : kx], (double)part);
@@ -474,6 +472,24 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
                             }
                         }
                     }
+                }
+            }
+            if (SINGLE) {  // one block-uniform branch on the output type, then eight stores at constant offsets from one pointer
+                const int o0 = warp * a.W + lane, dy = NW * a.W;
+                if (store_f) {
+                    float *op = out_f + o0;
+#pragma unroll
+                    for (int ky = 0; ky < KY; ky++)
+#pragma unroll
+                        for (int kx = 0; kx < KX; kx++)
+                            if (warp + NW * ky < th && lane + 32 * kx < tw) op[ky * dy + 32 * kx] = r1[SINGLE ? ky : 0][SINGLE ? kx : 0];
+                } else {
+                    double *op = out_d + o0;
+#pragma unroll
+                    for (int ky = 0; ky < KY; ky++)
+#pragma unroll
+                        for (int kx = 0; kx < KX; kx++)
+                            if (warp + NW * ky < th && lane + 32 * kx < tw) op[ky * dy + 32 * kx] = (double)r1[SINGLE ? ky : 0][SINGLE ? kx : 0];
                 }
             }
             __syncthreads();  // s0..s3 are reused by the next scale / channel
