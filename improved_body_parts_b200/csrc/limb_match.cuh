@@ -27,7 +27,7 @@ struct MatchArgs {
 };
 
 constexpr int kMatchThreads = 128;
-constexpr int kMatchRegF64 = 8;     // f64-plane path: (key, tie) pairs cached per lane
+constexpr int kMatchRegF64 = 16;    // f64-priority path: (key, tie) pairs cached per lane (x32 lanes = 512 per limb, as the f32 path)
 constexpr int kMatchRegCands = 16;  // survivor keys cached per lane (x32 lanes = 512 per limb)
 
 __device__ __forceinline__ bool key_better(double pa, int ia, double pb, int ib) {
@@ -191,6 +191,8 @@ __device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int
             case 3: m = match_rounds_f64<3>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
             case 4: m = match_rounds_f64<4>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
             case 5: case 6: m = match_rounds_f64<6>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 7: case 8: m = match_rounds_f64<8>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
+            case 9: case 10: case 11: case 12: m = match_rounds_f64<12>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
             default: m = match_rounds_f64<kMatchRegF64>(ws, cbase, o_ij, o_norm, nC, lim, lane); break;
         }
         __syncwarp();
