@@ -121,16 +121,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
     }
 }
 
-// Tuning form used by the persistent kernels: wait_ns == 0 is the hint wait above; wait_ns > 0 polls once and then sleeps
-// wait_ns between polls (fewer issue slots taken from the working warps, at the price of a later wake-up).
-__device__ __forceinline__ void mbar_wait_tuned(uint64_t *bar, uint32_t parity, int wait_ns) {
-    if (wait_ns <= 0) {
-        mbar_wait_sleep(bar, parity);
-        return;
-    }
-    while (!mbar_try_wait(bar, parity)) __nanosleep((unsigned)wait_ns);
-}
-
 // numpy's pairwise summation order for 8 <= n <= 128 (and the plain loop for n < 8): what both
 // `score_box.sum()` (f32) and `(score_box * grid).sum()` (f64) use in utils/util.py:206-211.
 template <typename T>

@@ -39,7 +39,6 @@ struct ScoreArgs {
     int debug;                                       // only read in -DSPG_DEBUG builds (timing experiments); always 0 otherwise
     int crit1_strict;                                // demo_image.py:288 compares with `>` where evaluate.py:246 uses `>=`
     int exact_warps;                                 // persistent kernel: scorer warps (the rest screen)
-    int wait_ns;                                     // persistent kernel: back-off of the role hand-off waits (0 = hint wait)
     double image_extent, thre2, connect_ration;
     Workspace ws;
 };

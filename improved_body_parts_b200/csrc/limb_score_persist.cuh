@@ -89,8 +89,6 @@ inline size_t persist_smem_bytes(size_t plane_bytes, int /*capP*/) {
     return kPersistPlaneOffset + kPersistSlots * plane + 128;
 }
 
-__device__ __forceinline__ bool cb_exists(int chunk, int npairs) { return chunk * 32 < npairs; }
-
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -107,71 +105,55 @@ struct ScreenCtx {
     float thre2;
 };
 
-// The conservative f32 screen of NP pairs per lane (limb_score.cuh explains why it may only report certain failures).
-// NP = 2 interleaves two independent pairs in one instruction stream: the per-sample dependency chain (FFMA -> FADD ->
-// shift -> IMAD -> LDS -> FSETP) is what bounds a screener warp, so a second chain in its shadow is almost free.
+// The conservative f32 screen of one pair (limb_score.cuh explains why it may only report certain failures).
 // Branch-free: a lane that takes no part (valid = false), a pair with an end point outside the map (x = -1), a
 // coincident pair or one whose sample count is within 0.01 of a rounding tie gets m = 0, whose table row has no
 // samples.  Every lane executes every sample up to the warp's maximum (rows are padded with a valid sample index),
 // so the samples are independent straight-line code.
-template <int NP>
-__device__ __forceinline__ void screen_pairs(const ScreenCtx &c, const int (&pc)[NP], const bool (&valid)[NP], int (&fails)[NP],
-                                             int (&qn)[NP], int (&maxfail)[NP]) {
-    float sx64[NP], sy64[NP], ax64o[NP], ay64o[NP];
-    const float *ts[NP];
-    int qmax_l = 0;
-#pragma unroll
-    for (int u = 0; u < NP; u++) {
-        const int i = c.nB > 1 ? (int)__umulhi((uint32_t)pc[u], c.magic) : pc[u];
-        const int jj = pc[u] - i * c.nB;
-        const float2 fa = c.ps->fa[i], fb = c.ps->fb[jj];
-        const float dx64 = fb.x - fa.x, dy64 = fb.y - fa.y;
-        const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
-        float rs;  // one MUFU.RSQ, no denormal fix-up: n2 below 1e-6 is not screened anyway
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(n2));
-        const float qf = n2 * rs + 1.0f;  // approximate norm + 1 (NaN for n2 = 0: falls out below)
-        const float r = rintf(qf);
-        const bool longp = qf >= (float)c.mid_num + 0.51f;
-        int m = longp ? c.mid_num : min((int)r, c.mid_num);
-        if (!longp && !(fabsf(qf - r) < 0.49f)) m = 0;  // m within 0.01 of a rounding tie -> survive
-        // coincident pairs and pairs with an end point outside the map are left to the exact path
-        if (!(n2 > 1e-6f) || !valid[u] || fminf(fa.x, fb.x) < 0.0f) m = 0;
-        m = max(m, 0);
-        const ScreenTab tb = c.tab[m];  // m = 0: no samples
-        qn[u] = tb.qn;
-        maxfail[u] = tb.maxfail;
-        sx64[u] = dx64 * tb.inv;
-        sy64[u] = dy64 * tb.inv;
-        // +33 folded into the start point: with u = pos + 33 (1/64 px), the pixel is u >> 6 for every sample that is not
-        // within {31,32,33} (mod 64) of a rounding boundary, i.e. u & 63 > 2
-        ax64o[u] = fa.x + 33.0f;
-        ay64o[u] = fa.y + 33.0f;
-        ts[u] = c.ts + m * kScreenSamples;
-        qmax_l = max(qmax_l, qn[u]);
-        fails[u] = 0;
-    }
-    const int qmax = __reduce_max_sync(0xffffffffu, qmax_l);
+__device__ __forceinline__ void screen_pair(const ScreenCtx &c, int pc, bool valid, int &fails, int &qn, int &maxfail) {
+    const int i = c.nB > 1 ? (int)__umulhi((uint32_t)pc, c.magic) : pc;
+    const int jj = pc - i * c.nB;
+    const float2 fa = c.ps->fa[i], fb = c.ps->fb[jj];
+    const float dx64 = fb.x - fa.x, dy64 = fb.y - fa.y;
+    const float n2 = (dx64 * dx64 + dy64 * dy64) * (1.0f / 4096.0f);  // px^2
+    float rs;  // one MUFU.RSQ, no denormal fix-up: n2 below 1e-6 is not screened anyway
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(n2));
+    const float qf = n2 * rs + 1.0f;  // approximate norm + 1 (NaN for n2 = 0: falls out below)
+    const float r = rintf(qf);
+    const bool longp = qf >= (float)c.mid_num + 0.51f;
+    int m = longp ? c.mid_num : min((int)r, c.mid_num);
+    if (!longp && !(fabsf(qf - r) < 0.49f)) m = 0;  // m within 0.01 of a rounding tie -> survive
+    // coincident pairs and pairs with an end point outside the map are left to the exact path
+    if (!(n2 > 1e-6f) || !valid || fminf(fa.x, fb.x) < 0.0f) m = 0;
+    m = max(m, 0);
+    const ScreenTab tb = c.tab[m];  // m = 0: no samples
+    qn = tb.qn;
+    maxfail = tb.maxfail;
+    const float sx64 = dx64 * tb.inv, sy64 = dy64 * tb.inv;
+    // +33 folded into the start point: with u = pos + 33 (1/64 px), the pixel is u >> 6 for every sample that is not
+    // within {31,32,33} (mod 64) of a rounding boundary, i.e. u & 63 > 2
+    const float ax64o = fa.x + 33.0f, ay64o = fa.y + 33.0f;
+    const float *ts = c.ts + m * kScreenSamples;
+    const int qmax = __reduce_max_sync(0xffffffffu, qn);
     // Round-to-nearest-even through the 1.5 * 2^23 trick (positions are in [0, 2^22)): the low bits of the float
     // pos + 1.5 * 2^23 are the rounded position u (an FADD instead of F2I, which runs on the quarter-rate conversion
     // pipe).  The bias is never subtracted: its low 6 bits are zero, so bits & 63 == u & 63, and bits >> 6 ==
     // (u >> 6) + kScreenBias; the kScreenBias * (W + 1) elements that adds to the index are taken off the plane's address once
-    // (the offset comes from shared memory so that it stays ONE register operand instead of being re-split into
-    // immediates at every sample)
+    // (kScreenBias; the offset comes from shared memory so that it stays ONE register operand instead of being
+    // re-split into immediates at every sample)
     const uint32_t base = c.base;
     // Every lane runs the warp's maximum number of samples; a lane with fewer samples of its own re-reads padded
     // entries of its row (its last sample, or sample 0 of the empty row), which can only repeat a failure it has
     // already counted -- so instead of masking those samples out one by one, the lane's tolerance is raised by their
     // number: more than maxfail + padded counted failures still means more than maxfail real ones.
+    fails = 0;
     auto sample = [&](int q2) {
-#pragma unroll
-        for (int u = 0; u < NP; u++) {
-            const float tf = ts[u][q2];
-            const uint32_t xb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sx64[u], ax64o[u]), 12582912.0f));
-            const uint32_t yb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sy64[u], ay64o[u]), 12582912.0f));
-            float v;
-            asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * ((yb >> 6) * (uint32_t)c.W + (xb >> 6))));
-            fails[u] += (int)(min(xb & 63u, yb & 63u) > 2u) & (int)!(v > c.thre2);
-        }
+        const float tf = ts[q2];
+        const uint32_t xb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sx64, ax64o), 12582912.0f));
+        const uint32_t yb = __float_as_uint(__fadd_rn(__fmaf_rn(tf, sy64, ay64o), 12582912.0f));
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * ((yb >> 6) * (uint32_t)c.W + (xb >> 6))));
+        fails += (int)(min(xb & 63u, yb & 63u) > 2u) & (int)!(v > c.thre2);
     };
     if (qmax == kScreenSamples) {  // the common case (a warp with at least one pair of >= mid_num samples): no trip checks
 #pragma unroll
@@ -183,13 +165,11 @@ __device__ __forceinline__ void screen_pairs(const ScreenCtx &c, const int (&pc)
             sample(q2);
         }
     }
-#pragma unroll
-    for (int u = 0; u < NP; u++) maxfail[u] += qmax - qn[u];
+    maxfail += qmax - qn;
 }
 
 // TA = float: f32 planes, f32 arithmetic; double: f32 planes evaluated in float64 (SPG_F32_AS_F64).
-// NP: pairs a screener lane screens at once (1, or 2 interleaved chunks per warp pass).
-template <typename TA, int NP>
+template <typename TA>
 __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(ScoreArgs a, int n_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // full: plane copy landed + lists published; screened: every screener has left the item -- its survivor list is
@@ -297,7 +277,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             const int s = j % kPersistSlots, e = j % kMetaSlots;
             if (j >= kPersistSlots) {  // the plane slot's previous item has been screened
                 const int jp = j - kPersistSlots;
-                mbar_wait_tuned(&bar_screened[jp % kMetaSlots], (jp / kMetaSlots) & 1, a.wait_ns);
+                mbar_wait_sleep(&bar_screened[jp % kMetaSlots], (jp / kMetaSlots) & 1);
             }
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / L, k = item - n_local * L;
@@ -312,7 +292,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
                 }
             }
             if (j >= kMetaSlots) {
-                mbar_wait_tuned(&bar_mfree[e], ((j / kMetaSlots) - 1) & 1, a.wait_ns);
+                mbar_wait_sleep(&bar_mfree[e], ((j / kMetaSlots) - 1) & 1);
                 close_item(j - kMetaSlots);
             }
             MetaSlot &ms = s_meta[e];
@@ -346,7 +326,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             if (j + 1 < nj) fetch(j + 1);              // in flight while the next iteration waits for its slots
         }
         for (int jp = max(0, nj - kMetaSlots); jp < nj; jp++) {  // the items still in the meta ring
-            mbar_wait_tuned(&bar_mfree[jp % kMetaSlots], (jp / kMetaSlots) & 1, a.wait_ns);
+            mbar_wait_sleep(&bar_mfree[jp % kMetaSlots], (jp / kMetaSlots) & 1);
             close_item(jp);
         }
     } else {
@@ -389,47 +369,32 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             for (int j = 0; j < nj; j++) {
                 const int s = j % kPersistSlots, e = j % kMetaSlots;
                 // `full` also means the meta slot's list and counters are recycled (the loader closed item j - kMetaSlots)
-                mbar_wait_tuned(&bar_full[s], (j / kPersistSlots) & 1, a.wait_ns);
+                mbar_wait_sleep(&bar_full[s], (j / kPersistSlots) & 1);
                 MetaSlot &ms = s_meta[e];
                 const int npairs = ms.hdr.npairs;
                 if (c0 * 32 < npairs) {  // warps without pairs skip the item
                     const T *plane = reinterpret_cast<const T *>(s_planes + s * plane_stride);
                     const ScreenCtx sc{&ms.peaks, smem_u32(plane) - *(volatile uint32_t *)&s_bias_bytes, s_tab, s_ts, W, a.mid_num,
                                        ms.hdr.nB, ms.hdr.magic, thre2};
-                    for (int c = c0; c * 32 < npairs; c += nS * NP) {
-                        int p[NP], pc[NP], fails[NP], qn[NP], maxfail[NP];
-                        bool keep[NP], valid[NP];
-#pragma unroll
-                        for (int u = 0; u < NP; u++) {
-                            const int cb = (c + u * nS) * 32;  // this lane's pair of chunk c + u * nS (which may not exist)
-                            p[u] = cb + lane;
-                            keep[u] = p[u] < npairs;
-                            pc[u] = min(p[u], npairs - 1);
-                            // a last chunk of only a few pairs (31 x 31 peaks leave 1) is not worth a pass: they go straight to
-                            // the exact phase, where they ride along in a chunk that exists anyway
-                            valid[u] = keep[u] && screen && npairs - cb > kScreenTailBypass;
+                    for (int c = c0; c * 32 < npairs; c += nS) {
+                        const int p = c * 32 + lane;
+                        bool keep = p < npairs;
+                        // a last chunk of only a few pairs (31 x 31 peaks leave 1) is not worth a pass: they go straight to
+                        // the exact phase, where they ride along in a chunk that exists anyway
+                        if (screen && npairs - c * 32 > kScreenTailBypass) {
+                            int fails, qn, maxfail;
+                            screen_pair(sc, min(p, npairs - 1), keep, fails, qn, maxfail);
+                            if (qn > 0) keep = fails <= maxfail;
                         }
-                        bool any = false;
-#pragma unroll
-                        for (int u = 0; u < NP; u++) any |= screen && cb_exists(c + u * nS, npairs) && npairs - (c + u * nS) * 32 > kScreenTailBypass;
-                        if (any) {  // warp-uniform
-                            screen_pairs<NP>(sc, pc, valid, fails, qn, maxfail);
-#pragma unroll
-                            for (int u = 0; u < NP; u++)
-                                if (qn[u] > 0) keep[u] = fails[u] <= maxfail[u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < NP; u++) {
-                            const uint32_t km = __ballot_sync(0xffffffffu, keep[u]);
-                            if (km) {
-                                int at = 0;
-                                if (lane == 0) at = atomicAdd(&ms.nsurv, __popc(km));
-                                at = __shfl_sync(0xffffffffu, at, 0);
-                                if (keep[u]) {
-                                    const int at_me = at + __popc(km & ((1u << lane) - 1u));
-                                    if (at_me < kPersistListCap) ms.list[at_me] = (uint16_t)p[u];
-                                    else exact_one(ms, plane, p[u]);  // list full: evaluate right here, from the staged plane
-                                }
+                        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+                        if (km) {
+                            int at = 0;
+                            if (lane == 0) at = atomicAdd(&ms.nsurv, __popc(km));
+                            at = __shfl_sync(0xffffffffu, at, 0);
+                            if (keep) {
+                                const int at_me = at + __popc(km & ((1u << lane) - 1u));
+                                if (at_me < kPersistListCap) ms.list[at_me] = (uint16_t)p;
+                                else exact_one(ms, plane, p);  // list full: evaluate right here, from the staged plane
                             }
                         }
                     }
@@ -442,7 +407,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) limb_score_persist_kernel(
             // =========================== scorers ===========================
             for (int j = 0; j < nj; j++) {
                 const int e = j % kMetaSlots;
-                mbar_wait_tuned(&bar_screened[e], (j / kMetaSlots) & 1, a.wait_ns);  // every screener has left item j: the list is complete
+                mbar_wait_sleep(&bar_screened[e], (j / kMetaSlots) & 1);  // every screener has left item j: the list is complete
                 MetaSlot &ms = s_meta[e];
                 const int ns = SPG_DBG(a.debug == 2) ? 0 : min(ms.nsurv, kPersistListCap);
                 if (ns > 0) {

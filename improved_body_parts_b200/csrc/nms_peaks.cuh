@@ -19,7 +19,6 @@ struct NmsArgs {
     const float *heat;
     int64_t img_stride, chan_stride;  // elements
     int H, W, band_rows, radius, use_bulk, image_base;
-    int wait_ns;                      // persistent kernel: back-off of the role hand-off waits (0 = hint wait)
     float thr;                        // (float)thre1: torch compares in f32 (util.py:182)
     Workspace ws;
 };

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
         if (lane == 0) {
             for (int j = 0; j < nj; j++) {
                 const int s = j % kNmsPSlots;
-                if (j >= kNmsPSlots) mbar_wait_tuned(&bar_free[s], ((j / kNmsPSlots) - 1) & 1, a.wait_ns);
+                if (j >= kNmsPSlots) mbar_wait_sleep(&bar_free[s], ((j / kNmsPSlots) - 1) & 1);
                 const int item = (int)blockIdx.x + j * G;
                 const int n_local = item / K, c = item - n_local * K;
                 const unsigned char *src =
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
         const float thr = a.thr;
         for (int j = 0; j < nj; j++) {
             const int s = j % kNmsPSlots, l = j % kNmsPLists;
-            mbar_wait_tuned(&bar_full[s], (j / kNmsPSlots) & 1, a.wait_ns);
-            if (j >= kNmsPLists) mbar_wait_tuned(&bar_lfree[l], ((j / kNmsPLists) - 1) & 1, a.wait_ns);
+            mbar_wait_sleep(&bar_full[s], (j / kNmsPSlots) & 1);
+            if (j >= kNmsPLists) mbar_wait_sleep(&bar_lfree[l], ((j / kNmsPLists) - 1) & 1);
             const float *buf = reinterpret_cast<const float *>(smem_raw + s * plane_stride);
             uint32_t *list = s_lists + (size_t)l * capP;
             // ---- pass 1: queue the float4 groups of this warp's slice that reach thre1.  First only the votes (one
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kNmsPThreads, 1) nms_peaks_persist_kernel(NmsA
         const int R = a.radius;
         for (int j = f; j < nj; j += kNmsPFinishers) {
             const int l = j % kNmsPLists;
-            mbar_wait_tuned(&bar_ready[l], (j / kNmsPLists) & 1, a.wait_ns);
+            mbar_wait_sleep(&bar_ready[l], (j / kNmsPLists) & 1);
             const uint32_t *list = s_lists + (size_t)l * capP;
             const int item = (int)blockIdx.x + j * G;
             const int n_local = item / K, c = item - n_local * K;

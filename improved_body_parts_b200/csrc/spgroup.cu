@@ -55,8 +55,6 @@ struct spg_handle {
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
     int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
-    int screen_ilp = 1;   // pairs a screener lane of the persistent limb_score handles at once (SPG_SCREEN_ILP = 1 | 2)
-    int wait_ns = 0;      // persistent kernels: explicit back-off between mbarrier polls (SPG_WAIT_NS; 0 = suspend-hint wait)
     int fuse_ma = 1;      // whole-path calls run the fused match+assemble kernel (SPG_FUSE_MA=0: the two kernels back to back)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
@@ -135,7 +133,6 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
     a.use_bulk = (W % 4 == 0) && (img_stride % 4 == 0) && (chan_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
     a.image_base = base;
     a.thr = (float)p->thre1;
-    a.wait_ns = h->wait_ns;
     a.ws = h->ws;
     if (h->persist && a.use_bulk && nms_persist_smem_bytes(H, W, h->ws.capP) <= h->smem_optin && (size_t)H * W / 4 < 65536 &&
         (size_t)H * W * sizeof(float) < (1u << 20) &&
@@ -171,15 +168,9 @@ int launch_score_t(spg_handle *h, const ScoreArgs &a, int n, cudaStream_t st) {
         persist_smem_bytes(plane_bytes, h->ws.capP) <= h->smem_optin) {
         // one resident CTA per SM walking a ring of 3 plane slots (loader / screeners / scorers)
         const size_t smem = persist_smem_bytes(plane_bytes, h->ws.capP);
-        if (h->screen_ilp == 2) {
-            SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_persist_kernel<TA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-            limb_score_persist_kernel<TA, 2><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
-            h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float,2>" : "limb_score_persist_kernel<double,2>";
-        } else {
-            SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_persist_kernel<TA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-            limb_score_persist_kernel<TA, 1><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
-            h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float,1>" : "limb_score_persist_kernel<double,1>";
-        }
+        SPG_CUDA(h, cudaFuncSetAttribute(limb_score_persist_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limb_score_persist_kernel<TA><<<std::min(grid, h->sm_count), kPersistThreads, smem, st>>>(a, grid);
+        h->stage_kernel[1] = sizeof(TA) == 4 ? "limb_score_persist_kernel<float>" : "limb_score_persist_kernel<double>";
     } else if (aligned && staged <= h->smem_optin) {
         SPG_CUDA(h, (cudaFuncSetAttribute(limb_score_kernel<T, true, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged)));
         limb_score_kernel<T, true, TA><<<grid, kScoreThreads, staged, st>>>(a);
@@ -215,7 +206,6 @@ int launch_score(spg_handle *h, const void *paf, int dtype, int64_t img_stride, 
     if (const char *e = getenv("SPG_DEBUG_PERSIST")) a.debug = atoi(e);
 #endif
     a.exact_warps = h->exact_warps;
-    a.wait_ns = h->wait_ns;
     a.ws = h->ws;
     h->cand_dtype = dtype;
     if (dtype == SPG_F64) return launch_score_t<double>(h, a, n, st);
@@ -374,8 +364,6 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
-    if (const char *e = getenv("SPG_SCREEN_ILP")) h->screen_ilp = atoi(e) == 2 ? 2 : 1;
-    if (const char *e = getenv("SPG_WAIT_NS")) h->wait_ns = std::max(0, std::min(100000, atoi(e)));
     if (const char *e = getenv("SPG_FUSE_MA")) h->fuse_ma = !(e[0] == '0');
     if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener
     DeviceGuard guard(h->device);

@@ -44,11 +44,8 @@ def measure(env):
 
 
 measure({})
-for w in (25, 50, 100, 200, 400, 800, 1600):
-    measure({"SPG_WAIT_NS": w})
 for ew in (10, 14):
     measure({"SPG_EXACT_WARPS": ew})
-for ew in (12, 14, 16, 18):
-    measure({"SPG_SCREEN_ILP": 2, "SPG_EXACT_WARPS": ew})
-measure({"SPG_SCREEN_ILP": 2, "SPG_EXACT_WARPS": 16, "SPG_WAIT_NS": 100})
+measure({"SPG_FUSE_MA": 0})
+measure({"SPG_PERSIST": 0})
 measure({})
