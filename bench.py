@@ -540,7 +540,8 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and args.config == "p30":
-        traffic = {k.replace(" ", "").replace("spg::", ""): v for k, v in json.load(open(tpath)).items()}.get(names[dom].replace(" ", ""))
+        tr = {k.replace(" ", "").replace("spg::", ""): v for k, v in json.load(open(tpath)).items()}
+        traffic = tr.get(names[dom].replace(" ", ""), tr.get(names[dom].split("<")[0]))  # ncu capture of the same kernel (template spelling may differ)
     path_bytes = B * (18 * 4 + 30 * esz) * H * W
     if alg_bytes[dom]:
         ach = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
