@@ -16,14 +16,15 @@
 
 namespace spg {
 
-constexpr int kMAMatchWarps = 7;
+constexpr int kMAMatchWarps = 7;   // default; the launch may use 1..15 (blockDim.x = 32 * (1 + matchers))
 constexpr int kMAThreads = 32 * (1 + kMAMatchWarps);
+constexpr int kMAMaxThreads = 512;
 
 inline size_t match_assemble_smem_bytes(int K, int L, int capP, int capR) {  // tables + person table + staged coordinates
     return assemble_conn_bytes(L, capP) + assemble_smem_bytes(K, capP, capR) + 2 * (size_t)K * capP * sizeof(double);
 }
 
-__global__ void __launch_bounds__(kMAThreads) match_assemble_kernel(AssembleArgs a, int keys_valid) {
+__global__ void __launch_bounds__(kMAMaxThreads) match_assemble_kernel(AssembleArgs a, int keys_valid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;  // unused in the fused form (the matchers fill the tables)
     __shared__ int s_ready[kMaxLimbs];
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(kMAThreads) match_assemble_kernel(AssembleArgs
     {   // CTA-wide prologue: person table + the image's refined coordinates into shared memory
         unsigned char *table_base = smem_raw + assemble_conn_bytes(L, capP);
         const PersonTable t = make_person_table(table_base, ws.K, capP, ws.capR);
-        init_person_table(t, ws, n, tid, kMAThreads, reinterpret_cast<double *>(table_base + assemble_smem_bytes(ws.K, capP, ws.capR)));
+        init_person_table(t, ws, n, tid, (int)blockDim.x, reinterpret_cast<double *>(table_base + assemble_smem_bytes(ws.K, capP, ws.capR)));
     }
     __syncthreads();
     if (warp == 0) {
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(kMAThreads) match_assemble_kernel(AssembleArgs
     double *s_cn = s_cs + LC;
     uint32_t *s_cij = reinterpret_cast<uint32_t *>(s_cn + LC);
     int *s_cc = reinterpret_cast<int *>(s_cij + LC);
-    for (int k = warp - 1; k < L; k += kMAMatchWarps) {
+    const int n_match = (int)blockDim.x / 32 - 1;
+    for (int k = warp - 1; k < L; k += n_match) {
         uint32_t *o_ij = s_cij + (size_t)k * capP;
         double *o_sc = s_cs + (size_t)k * capP, *o_nm = s_cn + (size_t)k * capP;
         const int m = match_limb(ws, n, k, lane, keys_valid != 0, o_ij, o_sc, o_nm);

@@ -55,6 +55,7 @@ struct spg_handle {
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
     int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
+    int ma_warps = kMAMatchWarps;  // matcher warps of the fused kernel (SPG_MA_WARPS, tuning)
     int fuse_ma = 1;      // whole-path calls run the fused match+assemble kernel (SPG_FUSE_MA=0: the two kernels back to back)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
     int stage = 0;  // 0 none, 1 peaks, 2 candidates, 3 connections, 4 people
@@ -278,7 +279,7 @@ int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, c
     }
     h->armed_flag = nullptr;  // one shot
     SPG_CUDA(h, cudaFuncSetAttribute(match_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    match_assemble_kernel<<<n, kMAThreads, smem, st>>>(a, h->cand_dtype == SPG_F32);
+    match_assemble_kernel<<<n, 32 * (1 + h->ma_warps), smem, st>>>(a, h->cand_dtype == SPG_F32);
     h->stage_kernel[2] = "match_assemble_kernel";
     h->stage_kernel[3] = "";
     h->launches++;
@@ -364,6 +365,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("SPG_NO_SCREEN")) h->screen = !(e[0] == '1');
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
+    if (const char *e = getenv("SPG_MA_WARPS")) h->ma_warps = std::max(1, std::min(15, atoi(e)));
     if (const char *e = getenv("SPG_FUSE_MA")) h->fuse_ma = !(e[0] == '0');
     if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener
     DeviceGuard guard(h->device);

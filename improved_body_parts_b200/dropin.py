@@ -77,9 +77,17 @@ def _check(r: GroupResult) -> None:
 
 
 def _maps_to_device(hwc: np.ndarray, channels: int, dtype):
+    """``[H, W, C]`` host maps (what predict() returns) -> ``[1, channels, H, W]`` device planes of ``dtype``.
+
+    The array goes up as it is and is transposed / cast on the device: a numpy transpose of a 512x512x30 float64 array
+    alone cost 40 ms per image (round 2 measurement).  The float64 -> float32 cast rounds to nearest even on both sides."""
     import torch
-    arr = np.ascontiguousarray(np.asarray(hwc)[:, :, :channels].transpose(2, 0, 1), dtype)
-    return torch.from_numpy(arr).to(f"cuda:{_device}")[None]
+    arr = np.asarray(hwc)
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(f"cuda:{_device}")
+    want = torch.float32 if dtype == np.float32 else torch.float64
+    return t[:, :, :channels].permute(2, 0, 1).to(want).contiguous()[None]
 
 
 class DeviceMaps:

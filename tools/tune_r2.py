@@ -29,7 +29,7 @@ def timeit(fn, iters=30):
 
 
 def measure(env):
-    for k in ("SPG_WAIT_NS", "SPG_EXACT_WARPS", "SPG_FUSE_MA", "SPG_PERSIST", "SPG_SCREEN_ILP"):
+    for k in ("SPG_MA_WARPS", "SPG_EXACT_WARPS", "SPG_FUSE_MA", "SPG_PERSIST"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     g = Grouper(max_batch=NB, max_person_rows=64)
@@ -46,6 +46,7 @@ def measure(env):
 measure({})
 for ew in (10, 14):
     measure({"SPG_EXACT_WARPS": ew})
+for mw in (2, 3, 4, 5, 6, 10, 15):
+    measure({"SPG_MA_WARPS": mw})
 measure({"SPG_FUSE_MA": 0})
-measure({"SPG_PERSIST": 0})
 measure({})
