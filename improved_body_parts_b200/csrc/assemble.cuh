@@ -288,6 +288,9 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
     bool overflow = false;
 
     for (int k = 0; k < L && !overflow; k++) {
+        SPG_TR(160 + 4 * k, 0);
+        int trace_rounds = 0;
+        (void)trace_rounds;
         if (FUSED) {  // acquire: limb k's rows and counter are in shared memory
             int r;
             do {
@@ -296,6 +299,7 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
             } while (!r);
         }
         const int cc = s_cc[k];
+        SPG_TR(160 + 4 * k + 1, cc);
         if (cc < 0) continue;  // special_k (:290)
         const int A = ws.limbs[2 * k], B = ws.limbs[2 * k + 1];
         for (int chunk = 0; chunk < cc && !overflow; chunk += 32) {
@@ -335,9 +339,13 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
                 nrows += __popc(creates);
                 pending &= ~emask;
                 __syncwarp();
+                trace_rounds++;
             }
         }
+        SPG_TR(160 + 4 * k + 2, nrows);
+        SPG_TRV(160 + 4 * k + 3, trace_rounds * 256 + cc);
     }
+    SPG_TR(300, nrows);
     if (FUSED && overflow) {  // the matchers may still be writing the tables this warp is about to reuse as staging space
         for (int k = 0; k < L; k++) {
             int r;
@@ -431,6 +439,7 @@ __device__ __forceinline__ void assemble_image(const AssembleArgs &a, unsigned c
         double *rows = reinterpret_cast<double *>(rec + 8);
         for (int i = lane; i < wn * WR; i += 32) rows[i] = s_wire[i];
     }
+    SPG_TR(301, 0);
     if (a.wire_flag != nullptr) {  // last CTA done publishes the step (the threadFenceReduction pattern, system scope)
         __syncwarp();              // every lane's record stores are ordered before lane 0's fence
         if (lane == 0) {

@@ -14,6 +14,25 @@
 
 namespace spg {
 
+// Clock trace of the first CTAs of a launch (development builds only: `make trace` -> libspgroup_trace.so, which is
+// never loaded by the package).  SPG_TR(slot, dep) stores clock64() once `dep` (any 32-bit value) is available.
+#ifdef SPG_TRACE
+constexpr int kTraceCtas = 64, kTraceSlots = 1024;
+__device__ unsigned long long g_spg_trace[kTraceCtas * kTraceSlots];
+__device__ __forceinline__ void trace_put(int slot, int dep, bool value_only) {
+    if (blockIdx.x < kTraceCtas && (threadIdx.x & 31) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+        g_spg_trace[blockIdx.x * kTraceSlots + slot] = value_only ? (unsigned long long)(unsigned)dep : t;
+    }
+}
+#define SPG_TR(slot, dep) ::spg::trace_put((slot), (int)(dep), false)
+#define SPG_TRV(slot, v) ::spg::trace_put((slot), (int)(v), true)
+#else
+#define SPG_TR(slot, dep) do {} while (0)
+#define SPG_TRV(slot, v) do {} while (0)
+#endif
+
 constexpr int kMaxParts = 32;        // K
 constexpr int kMaxLimbs = 64;        // L
 constexpr int kMaxCapPeaks = 128;    // peaks per (image, part); two 64-bit "used" masks in limb_match

@@ -141,6 +141,7 @@ __device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int
     const int nC = ws.cand_count[slot];
     const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
     if (nC < 0) return -1;  // special_k
+    SPG_TR(16 + 4 * k + 1, nC + (int)(key8[0] & 1ull));  // fused kernel's trace: counters and first key have arrived
     const int nA = min(cntA, ws.capP);
     const int nB = min(cntB, ws.capP);
     const int lim = min(nA, nB);

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kMAMaxThreads) match_assemble_kernel(AssembleA
     const int n = a.image_base + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = ws.L, capP = ws.capP;
+    SPG_TR(warp == 0 ? 0 : 2 + warp, 0);
     if (tid < L) s_ready[tid] = 0;
     {   // CTA-wide prologue: person table + the image's refined coordinates into shared memory
         unsigned char *table_base = smem_raw + assemble_conn_bytes(L, capP);
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(kMAMaxThreads) match_assemble_kernel(AssembleA
         init_person_table(t, ws, n, tid, (int)blockDim.x, reinterpret_cast<double *>(table_base + assemble_smem_bytes(ws.K, capP, ws.capR)));
     }
     __syncthreads();
+    if (warp == 0) SPG_TR(1, 0);
     if (warp == 0) {
         assemble_image<true>(a, smem_raw, bar, n, blockIdx.x, lane, s_ready);
         return;
@@ -54,8 +56,10 @@ __global__ void __launch_bounds__(kMAMaxThreads) match_assemble_kernel(AssembleA
     for (int k = warp - 1; k < L; k += n_match) {
         uint32_t *o_ij = s_cij + (size_t)k * capP;
         double *o_sc = s_cs + (size_t)k * capP, *o_nm = s_cn + (size_t)k * capP;
+        SPG_TR(16 + 4 * k, 0);
         const int m = match_limb(ws, n, k, lane, keys_valid != 0, o_ij, o_sc, o_nm);
         __syncwarp();
+        SPG_TR(16 + 4 * k + 2, m);
         // the stage-wise API (spg_download_connections, spg_assemble) reads the tables from global memory
         const size_t obase = ((size_t)n * L + k) * capP;
         for (int c = lane; c < m; c += 32) {
@@ -69,6 +73,7 @@ __global__ void __launch_bounds__(kMAMaxThreads) match_assemble_kernel(AssembleA
             s_cc[k] = m;
             asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(s_ready + k)), "r"(1) : "memory");
         }
+        SPG_TR(16 + 4 * k + 3, 0);
     }
 }
 

@@ -325,6 +325,19 @@ __global__ void wire_wait_kernel(const unsigned long long *word, unsigned long l
 
 extern "C" {
 
+#ifdef SPG_TRACE  // development builds only (make trace): the clock trace of the first CTAs of the last launches
+int spg_trace_read(unsigned long long *out, size_t n_words, int clear) {
+    const size_t n = std::min(n_words, (size_t)spg::kTraceCtas * spg::kTraceSlots);
+    if (cudaMemcpyFromSymbol(out, spg::g_spg_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (clear) {
+        void *p = nullptr;
+        if (cudaGetSymbolAddress(&p, spg::g_spg_trace) != cudaSuccess) return -1;
+        if (cudaMemset(p, 0, sizeof(spg::g_spg_trace)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
+
 int spg_abi_version(void) { return SPG_ABI_VERSION; }
 
 const char *spg_last_error(const spg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
