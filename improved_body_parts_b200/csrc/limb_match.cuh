@@ -141,7 +141,6 @@ __device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int
     const int nC = ws.cand_count[slot];
     const int cntA = ws.peak_count[(size_t)n * ws.K + pa], cntB = ws.peak_count[(size_t)n * ws.K + pb];
     if (nC < 0) return -1;  // special_k
-    SPG_TR(16 + 4 * k + 1, nC + (int)(key8[0] & 1ull));  // fused kernel's trace: counters and first key have arrived
     const int nA = min(cntA, ws.capP);
     const int nB = min(cntB, ws.capP);
     const int lim = min(nA, nB);
@@ -239,6 +238,176 @@ __device__ __forceinline__ int match_limb(const Workspace &ws, int n, int k, int
             m++;
         }
     }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same matching in PARALLEL rounds (the fused match+assemble kernel's matchers).
+//
+// Sequential greedy over a strict total order accepts exactly the candidates that are "locally dominant" once every
+// better candidate sharing an end point with them has been decided -- so it can run in rounds: every live candidate
+// posts its key on its two end points (shared-memory atomicMax), the candidates that hold the maximum on BOTH end points
+// are accepted together, everything sharing an end point with an accepted candidate dies, repeat.  A crowded limb
+// (30 x 30 peaks, ~80 candidates) needs 2-3 rounds instead of 30 strictly serial ones.  Which rows come out is the
+// same set; the ORDER find_people consumes them in (acceptance order = key descending, evaluate.py:259-268) is restored by
+// ranking the accepted keys.  The reference's stop at min(nA, nB) rows (:268) never cuts anything off: accepted rows use
+// distinct end points, so the count cannot exceed it, and once it is reached no candidate with two free end points is left.
+//
+// A key is two 32-bit words (priority bits, ~ij); the maximum is taken word by word: first the priority word, then --
+// among the candidates that tie on it -- the tie-break word.
+constexpr int kMatchLdSlots = 8;  // candidates per lane of the parallel form (x32 = 256 per limb; more: sequential rounds)
+
+__host__ __device__ inline size_t match_scratch_bytes(int capP) {  // per matcher warp
+    return (((size_t)capP * (sizeof(unsigned long long) + 4 * sizeof(uint2) + sizeof(int) + 2)) + 15) & ~(size_t)15;
+}
+
+struct MatchScratch {
+    unsigned long long *acc_key;  // [capP] accepted keys, unordered
+    uint2 *best;                  // [2 sets][2 sides][capP] (priority word, tie-break word) maxima; the sets alternate by round
+    int *acc_cidx;                // [capP] candidate index of each accepted key
+    unsigned char *used;          // [2 sides][capP]
+};
+__device__ __forceinline__ MatchScratch make_match_scratch(unsigned char *base, int capP) {
+    MatchScratch s;
+    s.acc_key = reinterpret_cast<unsigned long long *>(base);
+    s.best = reinterpret_cast<uint2 *>(s.acc_key + capP);
+    s.acc_cidx = reinterpret_cast<int *>(s.best + 4 * (size_t)capP);
+    s.used = reinterpret_cast<unsigned char *>(s.acc_cidx + capP);
+    return s;
+}
+
+template <int NS>
+__device__ __forceinline__ int match_rounds_ld(const MatchScratch &sc, int capP, const unsigned long long (&key8)[kMatchRegCands], int nC,
+                                               int lane, int tr) {
+    (void)tr;
+    int tr_round = 0;
+    (void)tr_round;
+    for (int e = lane; e < 2 * capP; e += 32) {  // set 0 of the maxima, the used flags
+        sc.best[e] = make_uint2(0u, 0u);
+        sc.used[e] = 0;
+    }
+    uint32_t alive = 0u;
+#pragma unroll
+    for (int r = 0; r < NS; r++) alive |= (lane + 32 * r < nC) ? (1u << r) : 0u;
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    int m = 0, cur = 0;
+    SPG_TR(tr + 0, alive);
+    for (;;) {
+        uint2 *bA = sc.best + (size_t)(2 * cur) * capP, *bB = bA + capP;
+        uint2 *zA = sc.best + (size_t)(2 * (cur ^ 1)) * capP, *zB = zA + capP;
+        // (a) candidates whose end point was taken last round die; the others post their priority word and clear the
+        //     entries of the other set for the next round
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            if ((alive >> r) & 1u) {
+                const uint32_t ij = ~(uint32_t)key8[r];
+                const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
+                if (sc.used[i] | sc.used[capP + j]) {
+                    alive &= ~(1u << r);
+                } else {
+                    const uint32_t hi = (uint32_t)(key8[r] >> 32);
+                    atomicMax(&bA[i].x, hi);
+                    atomicMax(&bB[j].x, hi);
+                    zA[i] = make_uint2(0u, 0u);
+                    zB[j] = make_uint2(0u, 0u);
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive != 0u)) break;
+        __syncwarp();
+        // (b) among the holders of an end point's best priority word: the tie-break word
+        uint32_t topA = 0u, topB = 0u;
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            if ((alive >> r) & 1u) {
+                const uint32_t lo = (uint32_t)key8[r], hi = (uint32_t)(key8[r] >> 32);
+                const uint32_t ij = ~lo;
+                const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
+                if (bA[i].x == hi) { topA |= 1u << r; atomicMax(&bA[i].y, lo); }
+                if (bB[j].x == hi) { topB |= 1u << r; atomicMax(&bB[j].y, lo); }
+            }
+        }
+        __syncwarp();
+        // (c) best on both end points: accepted
+#pragma unroll
+        for (int r = 0; r < NS; r++) {
+            bool dom = false;
+            const uint32_t lo = (uint32_t)key8[r];
+            const uint32_t ij = ~lo;
+            const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
+            if ((alive & topA & topB) >> r & 1u) dom = bA[i].y == lo && bB[j].y == lo;
+            const uint32_t bm = __ballot_sync(0xffffffffu, dom);
+            if (dom) {
+                const int pos = m + __popc(bm & lt);
+                sc.acc_key[pos] = key8[r];
+                sc.acc_cidx[pos] = lane + 32 * r;
+                sc.used[i] = 1;
+                sc.used[capP + j] = 1;
+                alive &= ~(1u << r);
+            }
+            m += __popc(bm);
+        }
+        __syncwarp();
+        cur ^= 1;
+        if (tr_round < 4) SPG_TR(tr + 1 + tr_round, m);
+        tr_round++;
+    }
+    __syncwarp();
+    SPG_TRV(tr + 7, tr_round * 1024 + nC);
+    return m;
+}
+
+// One (image, limb) by one warp of the fused kernel: rows to o_ij / o_score / o_norm in acceptance order.  (ax, ay, bx, by)
+// are the refined coordinates of the limb's two peak lists (the kernel's shared-memory copy).  Limbs the parallel form
+// does not cover (f64 priorities, more than 32 * kMatchLdSlots candidates) take the sequential rounds of match_limb.
+__device__ __forceinline__ int match_limb_ld(const Workspace &ws, int n, int k, int lane, bool keys_valid, uint32_t *o_ij, double *o_score,
+                                             double *o_norm, const double *ax, const double *ay, const double *bx, const double *by,
+                                             unsigned char *scratch, uint64_t *coords_bar) {
+    if (!keys_valid) return match_limb(ws, n, k, lane, keys_valid, o_ij, o_score, o_norm);
+    const size_t slot = (size_t)n * ws.L + k;
+    const size_t cbase = slot * ws.capC;
+    unsigned long long key8[kMatchRegCands];
+#pragma unroll
+    for (int r = 0; r < kMatchLdSlots; r++) {  // speculative, as in match_limb: one round trip to L2
+        const int cidx = lane + 32 * r;
+        key8[r] = cidx < ws.capC ? ws.cand_key[cbase + cidx] : 0ull;
+    }
+#pragma unroll
+    for (int r = kMatchLdSlots; r < kMatchRegCands; r++) key8[r] = 0ull;
+    const int nC = ws.cand_count[slot];
+    if (nC < 0) return -1;  // special_k
+    SPG_TR(16 + 4 * k + 1, nC + (int)(key8[0] & 1ull));
+    if (nC > 32 * kMatchLdSlots) return match_limb(ws, n, k, lane, keys_valid, o_ij, o_score, o_norm);
+    const MatchScratch sc = make_match_scratch(scratch, ws.capP);
+    const int nslots = (nC + 31) >> 5;
+    int m = 0;
+    switch (nslots) {
+        case 0: break;
+        case 1: m = match_rounds_ld<1>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        case 2: m = match_rounds_ld<2>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        case 3: m = match_rounds_ld<3>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        case 4: m = match_rounds_ld<4>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        case 5: case 6: m = match_rounds_ld<6>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        default: m = match_rounds_ld<kMatchLdSlots>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+    }
+    SPG_TR(400 + 8 * k + 5, m);
+    if (coords_bar) mbar_wait(coords_bar, 0);  // the staged coordinates (a bulk copy issued at kernel start) have landed
+    // acceptance order = key descending: a row's position is the number of accepted keys above its own
+    for (int e = lane; e < m; e += 32) {
+        const unsigned long long ke = sc.acc_key[e];
+        const double score = ws.cand_score[cbase + sc.acc_cidx[e]];  // in flight during the ranking
+        int rank = 0;
+        for (int f = 0; f < m; f++) rank += sc.acc_key[f] > ke ? 1 : 0;
+        const uint32_t ij = ~(uint32_t)ke;
+        const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
+        const double vx = __dsub_rn(bx[j], ax[i]), vy = __dsub_rn(by[j], ay[i]);
+        o_ij[rank] = ij;
+        o_score[rank] = score;
+        o_norm[rank] = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    }
+    __syncwarp();
+    SPG_TR(400 + 8 * k + 6, m);
     return m;
 }
 

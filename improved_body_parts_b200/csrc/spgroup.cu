@@ -55,6 +55,7 @@ struct spg_handle {
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
     int exact_warps = 12; // scorer warps of the persistent limb_score (SPG_EXACT_WARPS)
+    int post_generic_ident = 0;  // SPG_POST_IDENT=0: single-scale identity configurations take postnet_kernel<true,true,*> (A/B timing)
     int ma_warps = kMAMatchWarps;  // matcher warps of the fused kernel (SPG_MA_WARPS, tuning)
     int fuse_ma = 1;      // whole-path calls run the fused match+assemble kernel (SPG_FUSE_MA=0: the two kernels back to back)
     int cand_dtype = SPG_F32;  // dtype of the planes the current candidates were scored on
@@ -270,8 +271,8 @@ int launch_match_assemble(spg_handle *h, int base, int n, const spg_params *p, c
     a.wire_flag = h->armed_flag; a.wire_flag_value = h->armed_value; a.done_counter = h->done_counter;
     a.ws = h->ws;
     a.ws.wire_first += base;
-    a.use_bulk = 0;
-    const size_t smem = match_assemble_smem_bytes(h->ws.K, h->ws.L, h->ws.capP, h->ws.capR);
+    a.use_bulk = ((size_t)h->ws.K * h->ws.capP * sizeof(float)) % 16 == 0;  // bulk copies move multiples of 16 bytes
+    const size_t smem = match_assemble_smem_bytes(h->ws.K, h->ws.L, h->ws.capP, h->ws.capR, h->ma_warps);
     if (smem > h->smem_optin) {  // very large capacities: the two stand-alone kernels need less shared memory
         int rc;
         if ((rc = launch_match(h, base, n, st))) return rc;
@@ -380,6 +381,7 @@ int spg_create(const spg_config *cfg, spg_handle **out) {
     if (const char *e = getenv("SPG_PERSIST")) h->persist = !(e[0] == '0');  // 0: per-item kernels only (A/B tests)
     if (const char *e = getenv("SPG_MA_WARPS")) h->ma_warps = std::max(1, std::min(15, atoi(e)));
     if (const char *e = getenv("SPG_FUSE_MA")) h->fuse_ma = !(e[0] == '0');
+    if (const char *e = getenv("SPG_POST_IDENT")) h->post_generic_ident = atoi(e) == 0;
     if (const char *e = getenv("SPG_EXACT_WARPS")) h->exact_warps = std::max(1, std::min(30, atoi(e)));  // the kernel keeps >= 1 screener
     DeviceGuard guard(h->device);
 
@@ -683,7 +685,17 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
         SPG_CUDA(h, (cudaFuncSetAttribute(postnet_kernel<S_, I_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))); \
         postnet_kernel<S_, I_, F_><<<grid, kPostThreads, smem, st>>>(a);                                                      \
     } while (0)
-            if (single) {
+            if (single && ident && !h->post_generic_ident) {  // the reference's default: its own kernel (two passes, per-thread state hoisted)
+                a.tile_w = kPostI_TW; a.tile_h = kPostI_TH;
+                a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
+                a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
+                const long long tiles_i = (long long)a.tiles_x * a.tiles_y * n;
+                const int chunks_i = (int)std::min<long long>(a.n_out, std::max<long long>(1, ((long long)h->sm_count * 32 + tiles_i - 1) / tiles_i));
+                a.chan_chunk = (a.n_out + chunks_i - 1) / chunks_i;
+                dim3 grid_i((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
+                if (all16) postnet_x4_ident_kernel<true><<<grid_i, kPostThreads, 0, st>>>(a);
+                else postnet_x4_ident_kernel<false><<<grid_i, kPostThreads, 0, st>>>(a);
+            } else if (single) {
                 if (ident) { if (all16) SPG_POST_LAUNCH(true, true, true); else SPG_POST_LAUNCH(true, true, false); }
                 else { if (all16) SPG_POST_LAUNCH(true, false, true); else SPG_POST_LAUNCH(true, false, false); }
             } else {

@@ -62,6 +62,11 @@ print("assembler per image: wait %.0f  work %.0f   | per limb work %.0f, rounds 
     wait.sum(1).mean(), work.sum(1).mean(), work.mean(), rounds.mean(), conns.mean(), work.sum() / max(rounds.sum(), 1)))
 print("matcher per limb: load %.0f  rounds %.0f  publish %.0f   (conns %.1f -> %.0f cycles per accepted row)" % (
     mload.mean(), mrun.mean(), mpub.mean(), conns.mean(), mrun.sum() / max(conns.sum(), 1)))
+print("matcher detail, CTA 0 (cycles from the limb's start): init, after round 1..4, rounds done, rows out | rounds, candidates")
+for k in range(L):
+    t = tr[0]; b = 400 + 8 * k; st = t[16 + 4 * k]
+    f = lambda v: int(v - st) if v else -1
+    print("%3d | %6d | %6d %6d %6d %6d | %6d %6d | %d rounds, %d candidates" % (k, f(t[b]), f(t[b + 1]), f(t[b + 2]), f(t[b + 3]), f(t[b + 4]), f(t[b + 5]), f(t[b + 6]), int(t[b + 7]) >> 10, int(t[b + 7]) & 1023))
 print("limb  wait  work rounds conns | m_start m_loaded m_done m_pub   (CTA 0)")
 for l in res[0]["limbs"]:
     print("%3d %6d %6d %3d %3d | %7s %7s %7s %7s | asm %7s %7s %7s" % (

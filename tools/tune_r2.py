@@ -44,6 +44,9 @@ def measure(env):
 
 
 measure({})
+if len(sys.argv) > 2:   # "quick": the default only
+    measure({"SPG_FUSE_MA": 0})
+    sys.exit(0)
 for ew in (10, 14):
     measure({"SPG_EXACT_WARPS": ew})
 for mw in (2, 3, 4, 5, 6, 10, 15):
