@@ -431,50 +431,68 @@ __device__ __forceinline__ void emit_people(const AssembleArgs &a, const PersonT
     }
     __syncthreads();
     const int out = *s_out;
-    // one warp per row, one lane per column
-    for (int j = warp; j < nrows; j += nwarps) {
+    // one thread per (row, column): `subset` rows (K + 2 columns of two doubles), then the joints (J columns), a group of
+    // nthreads / columns rows per pass -- the thread's column and row-in-group are fixed, so a pass is a flag lookup,
+    // two 16-byte loads and one 16-byte store
+    {
+        // (K + 2 > nthreads -- 32 parts in the one-warp stand-alone kernel -- : two column passes per row)
+        const int cols = RS, rows_pp = max(nthreads / cols, 1);
+        const int jr = tid / cols;
+        for (int col = tid - jr * cols; col < cols; col += nthreads)
+            for (int j = jr; j < nrows && jr < rows_pp; j += rows_pp) {
+                const int tj = keep_pos[j];
+                if (tj == 0) continue;
+                const RowRec r = load_row(t.row + j);
+                double2 v;
+                if (col < K) {
+                    SlotRec sl;
+                    sl.sc = -1.0; sl.id = -1; sl.pad = 0;
+                    if ((r.mask >> col) & 1u) sl = load_slot(t.slot + col * capR + j);
+                    v = make_double2((double)sl.id, sl.sc);
+                } else if (col == K) {
+                    v = make_double2(r.total, -1.0);
+                } else {
+                    v = make_double2((double)r.cnt, r.maxlen);
+                }
+                reinterpret_cast<double2 *>(g_subset)[(size_t)(tj - 2) * RS + col] = v;
+            }
+    }
+    if (J > 0) {
+        const int rows_pp = nthreads / J;
+        const int jr = tid / J, g = tid - jr * J;
+        if (jr < rows_pp) {
+            const int part = ws.out_from_part[g];
+            const int offp = t.off[part];
+            for (int j = jr; j < nrows; j += rows_pp) {
+                const int tj = keep_pos[j];
+                if (tj == 0) continue;
+                const int o = tj - 2;
+                double x = 0.0, y = 0.0;  // :523-539
+                if ((t.row[j].mask >> part) & 1u) {
+                    const int idx = t.slot[part * capR + j].id - offp;
+                    x = t.px[part * capP + idx];
+                    y = t.py[part * capP + idx];
+                }
+                reinterpret_cast<double2 *>(g_xy)[(size_t)o * J + g] = make_double2(x, y);
+                if (wire_on && o < ws.wire_rows) {
+                    s_wire[(size_t)o * WR + 2 * g + 0] = x;
+                    s_wire[(size_t)o * WR + 2 * g + 1] = y;
+                }
+            }
+        }
+    }
+    for (int j = tid; j < nrows; j += nthreads) {  // person score and presence mask
         const int tj = keep_pos[j];
         if (tj == 0) continue;
         const int o = tj - 2;
-        const RowRec r = load_row(t.row + j);
-        const uint32_t mj = r.mask;
-        double2 *row = reinterpret_cast<double2 *>(g_subset + (size_t)o * RS * 2);
-        if (lane < K) {
-            const bool has = (mj >> lane) & 1u;
-            SlotRec sl;
-            sl.sc = -1.0; sl.id = -1; sl.pad = 0;
-            if (has) sl = load_slot(t.slot + lane * capR + j);
-            row[lane] = make_double2((double)sl.id, sl.sc);
-        } else if (lane == K) {
-            row[K] = make_double2(r.total, -1.0);
-        } else if (lane == K + 1) {
-            row[K + 1] = make_double2((double)r.cnt, r.maxlen);
-        }
-        const bool wrow = wire_on && o < ws.wire_rows;
-        bool present = false;
-        if (lane < J) {  // :523-539
-            const int part = ws.out_from_part[lane];
-            double x = 0.0, y = 0.0;
-            if ((mj >> part) & 1u) {
-                const int idx = t.slot[part * capR + j].id - t.off[part];
-                x = t.px[part * capP + idx];
-                y = t.py[part * capP + idx];
-                present = true;
-            }
-            reinterpret_cast<double2 *>(g_xy)[(size_t)o * J + lane] = make_double2(x, y);
-            if (wrow) {
-                s_wire[(size_t)o * WR + 2 * lane + 0] = x;
-                s_wire[(size_t)o * WR + 2 * lane + 1] = y;
-            }
-        }
-        const uint32_t pm = __ballot_sync(0xffffffffu, present);
-        if (lane == 0) {
-            const double pscore = t.pscore[j];
-            g_score[o] = pscore;
-            if (wrow) {
-                s_wire[(size_t)o * WR + 2 * J] = pscore;
-                reinterpret_cast<unsigned long long *>(s_wire)[(size_t)o * WR + 2 * J + 1] = (unsigned long long)pm;
-            }
+        const double pscore = t.pscore[j];
+        g_score[o] = pscore;
+        if (wire_on && o < ws.wire_rows) {
+            const uint32_t mj = t.row[j].mask;
+            unsigned long long pm = 0ull;
+            for (int g = 0; g < J; g++) pm |= (unsigned long long)((mj >> ws.out_from_part[g]) & 1u) << g;
+            s_wire[(size_t)o * WR + 2 * J] = pscore;
+            reinterpret_cast<unsigned long long *>(s_wire)[(size_t)o * WR + 2 * J + 1] = pm;
         }
     }
     if (ws.wire != nullptr && (!wire_on || out > ws.wire_rows)) flags |= kStWireOverflow;

@@ -278,7 +278,7 @@ __device__ __forceinline__ MatchScratch make_match_scratch(unsigned char *base, 
 
 template <int NS>
 __device__ __forceinline__ int match_rounds_ld(const MatchScratch &sc, int capP, const unsigned long long (&key8)[kMatchRegCands], int nC,
-                                               int lane, int tr) {
+                                               int lane, int tr, const double *score_base) {
     (void)tr;
     int tr_round = 0;
     (void)tr_round;
@@ -342,6 +342,7 @@ __device__ __forceinline__ int match_rounds_ld(const MatchScratch &sc, int capP,
                 const int pos = m + __popc(bm & lt);
                 sc.acc_key[pos] = key8[r];
                 sc.acc_cidx[pos] = lane + 32 * r;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(score_base + lane + 32 * r));  // read when the rows are written out
                 sc.used[i] = 1;
                 sc.used[capP + j] = 1;
                 alive &= ~(1u << r);
@@ -384,12 +385,12 @@ __device__ __forceinline__ int match_limb_ld(const Workspace &ws, int n, int k, 
     int m = 0;
     switch (nslots) {
         case 0: break;
-        case 1: m = match_rounds_ld<1>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
-        case 2: m = match_rounds_ld<2>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
-        case 3: m = match_rounds_ld<3>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
-        case 4: m = match_rounds_ld<4>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
-        case 5: case 6: m = match_rounds_ld<6>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
-        default: m = match_rounds_ld<kMatchLdSlots>(sc, ws.capP, key8, nC, lane, 400 + 8 * k); break;
+        case 1: m = match_rounds_ld<1>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
+        case 2: m = match_rounds_ld<2>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
+        case 3: m = match_rounds_ld<3>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
+        case 4: m = match_rounds_ld<4>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
+        case 5: case 6: m = match_rounds_ld<6>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
+        default: m = match_rounds_ld<kMatchLdSlots>(sc, ws.capP, key8, nC, lane, 400 + 8 * k, ws.cand_score + cbase); break;
     }
     SPG_TR(400 + 8 * k + 5, m);
     if (coords_bar) mbar_wait(coords_bar, 0);  // the staged coordinates (a bulk copy issued at kernel start) have landed
