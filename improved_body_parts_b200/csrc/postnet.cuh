@@ -520,23 +520,23 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
 // one can store straight to the maps.  This kernel is postnet_kernel<true, true, F16> with everything that does not
 // depend on the channel hoisted out of the channel loop: a thread keeps its five clamped tap offsets of either pass, the
 // four weight sets and its global offsets in registers, so a channel costs it the source loads, one item of the
-// horizontal pass (5 shared loads, 28 flops, one 16-byte shared store) and two of the vertical pass (5 shared loads, 28
-// flops, 4 global stores each) -- ~20 instructions per output pixel instead of ~80.  Same operations in the same order
-// on every value: identical maps.
-constexpr int kPostI_TW = 64, kPostI_TH = 32;       // output tile
+// horizontal pass (6 shared loads, 56 flops, two 16-byte shared stores) and one of the vertical pass (five 16-byte shared
+// loads, 112 flops, four 16-byte global stores: 16 output pixels) -- ~16 instructions per output pixel instead of ~80.
+// Same operations in the same order on every value: identical maps.
+constexpr int kPostI_TW = 128, kPostI_TH = 32;      // output tile
 constexpr int kPostI_Q = kPostI_TW / 4, kPostI_P = kPostI_TH / 4;
 constexpr int kPostI_RS = kPostI_P + 4, kPostI_CS = kPostI_Q + 4;  // source tile (network resolution): groups p-2 .. p+2
-constexpr int kPostI_S0 = 20;                       // row stride of the source tile in shared memory
+constexpr int kPostI_S0 = kPostI_CS;                // row stride of the source tile in shared memory
+constexpr int kPostI_LD = (kPostI_RS * kPostI_CS + kPostThreads - 1) / kPostThreads;  // source elements per thread
 
 template <bool F16>
 __global__ void __launch_bounds__(kPostThreads, 4) postnet_x4_ident_kernel(PostArgs a) {
-    __shared__ float s0[kPostI_RS * kPostI_S0];
-    __shared__ __align__(16) float s1[2][kPostI_RS * kPostI_TW];   // after the horizontal pass; two buffers: one barrier less per channel
-    __shared__ int s_o1x[kPostI_Q][5], s_o1y[kPostI_P][5];
+    __shared__ float s0[2][kPostI_RS * kPostI_S0];                  // source tile, flip-averaged
+    __shared__ __align__(16) float s1[2][kPostI_RS * kPostI_TW];   // after the horizontal pass
+    __shared__ int s_o1x[kPostI_Q + 1][5], s_o1y[kPostI_P][5];
     __shared__ float4 s_wph[4];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kPostThreads / 32;
+    const int tid = threadIdx.x;
     const PostScale &S = a.sc[0];
     const int tile = blockIdx.x, n = blockIdx.z;
     const int c_begin = blockIdx.y * a.chan_chunk, c_end = min(c_begin + a.chan_chunk, a.n_out);
@@ -547,125 +547,169 @@ __global__ void __launch_bounds__(kPostThreads, 4) postnet_x4_ident_kernel(PostA
     const int q_lo = ox0 >> 2, Q = ((ox0 + tw - 1) >> 2) - q_lo + 1, p_lo = oy0 >> 2, P = ((oy0 + th - 1) >> 2) - p_lo + 1;
     const int sc_lo = max(q_lo - 2, 0), sc_hi = min(q_lo + Q + 1, S.w - 1), sr_lo = max(p_lo - 2, 0), sr_hi = min(p_lo + P + 1, S.h - 1);
     const int CS = sc_hi - sc_lo + 1, RS = sr_hi - sr_lo + 1;
-    if (tid < Q) {
+    if (tid <= Q && tid <= kPostI_Q) {  // (one entry past the last group: the pair (q, q + 1) of pass 1 reads it)
 #pragma unroll
         for (int k = 0; k < 5; k++) s_o1x[tid][k] = clampi(q_lo + tid - 2 + k, 0, S.w - 1) - sc_lo;
-    } else if (tid >= 32 && tid < 32 + P) {
+    } else if (tid >= 64 && tid < 64 + P) {
 #pragma unroll
-        for (int k = 0; k < 5; k++) s_o1y[tid - 32][k] = (clampi(p_lo + tid - 32 - 2 + k, 0, S.h - 1) - sr_lo) * kPostI_TW;
-    } else if (tid >= 64 && tid < 68) {
+        for (int k = 0; k < 5; k++) s_o1y[tid - 64][k] = (clampi(p_lo + tid - 64 - 2 + k, 0, S.h - 1) - sr_lo) * kPostI_TW;
+    } else if (tid >= 96 && tid < 100) {
         float cc[4];
-        axis_entry(4 + (tid - 64), 0.25, cc);  // destination 4 + r: the same fraction as every 4q + r
-        s_wph[tid - 64] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        axis_entry(4 + (tid - 96), 0.25, cc);  // destination 4 + r: the same fraction as every 4q + r
+        s_wph[tid - 96] = make_float4(cc[0], cc[1], cc[2], cc[3]);
     }
     __syncthreads();
     const float4 W0 = s_wph[0], W1 = s_wph[1], W2 = s_wph[2], W3 = s_wph[3];
-    // pass 1 item of this thread: source row i1, group q1
-    const int i1 = tid >> 4, q1 = tid & 15;
+    // pass 1 item of this thread: source row i1, the two groups q1, q1 + 1 (six source values in, eight columns out)
+    const int i1 = tid >> 4, q1 = 2 * (tid & 15);
     const bool act1 = i1 < RS && q1 < Q;
-    int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0;
     if (act1) {
         const int b = i1 * kPostI_S0;
         h0 = b + s_o1x[q1][0]; h1 = b + s_o1x[q1][1]; h2 = b + s_o1x[q1][2]; h3 = b + s_o1x[q1][3]; h4 = b + s_o1x[q1][4];
+        h5 = b + s_o1x[q1 + 1][4];
     }
     const int d1 = i1 * kPostI_TW + 4 * q1;
-    // pass 2 items: column X2, row groups p2 and p2 + 4
-    const int X2 = tid & 63, p2 = tid >> 6;
-    int v0[2], v1[2], v2[2], v3[2], v4[2];
-    bool act2[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const int p = p2 + 4 * u;
-        act2[u] = p < P && X2 < tw;
-        const int pp = min(p, P - 1);
-        v0[u] = s_o1y[pp][0] + X2; v1[u] = s_o1y[pp][1] + X2; v2[u] = s_o1y[pp][2] + X2; v3[u] = s_o1y[pp][3] + X2; v4[u] = s_o1y[pp][4] + X2;
+    // pass 2 item: row group p2, columns 4 * x2 .. 4 * x2 + 3 (five 16-byte loads in, four rows of four columns out)
+    const int p2 = tid >> 5, x2 = tid & 31;
+    const bool act2 = p2 < P && 4 * x2 < tw;
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+    if (act2) {
+        v0 = s_o1y[p2][0] + 4 * x2; v1 = s_o1y[p2][1] + 4 * x2; v2 = s_o1y[p2][2] + 4 * x2; v3 = s_o1y[p2][3] + 4 * x2; v4 = s_o1y[p2][4] + 4 * x2;
     }
-    const bool full = tw == kPostI_TW && th == kPostI_TH;
-    // source loads of this thread: rows warp, warp + NW of the tile, column lane
-    constexpr int KI = (kPostI_RS + NW - 1) / NW;
-    long long g0[KI], g1[KI];
-    bool actl[KI];
+    // 16-byte stores need all of the tile's columns and 16-byte aligned rows (W a multiple of 4; float64 rows: always then)
+    const bool vec = tw == kPostI_TW && (a.W & 3) == 0;
+    // source elements of this thread (row-major over the RS x CS tile)
+    long long g0[kPostI_LD], g1[kPostI_LD];
+    int sdst[kPostI_LD];
+    bool actl[kPostI_LD];
 #pragma unroll
-    for (int ki = 0; ki < KI; ki++) {
-        const int i = warp + NW * ki;
-        actl[ki] = i < RS && lane < CS;
-        g0[ki] = (long long)n * S.img_stride + (long long)(sr_lo + i) * S.w + sc_lo + lane;
-        g1[ki] = (long long)n * S.img_stride + S.pair_stride + (long long)(sr_lo + i) * S.w + (S.w - 1 - sc_lo) - lane;
+    for (int u = 0; u < kPostI_LD; u++) {
+        const int e = tid + kPostThreads * u;
+        const int i = e / CS, j = e - i * CS;
+        actl[u] = i < RS;
+        sdst[u] = i * kPostI_S0 + j;
+        g0[u] = (long long)n * S.img_stride + (long long)(sr_lo + i) * S.w + sc_lo + j;
+        g1[u] = (long long)n * S.img_stride + S.pair_stride + (long long)(sr_lo + i) * S.w + (S.w - 1 - sc_lo) - j;
     }
-    float pv0[KI], pv1[KI];
+    float pv0[kPostI_LD], pv1[kPostI_LD];
     auto prefetch = [&](int c) {
         const long long c0 = (long long)a.src_chan[c] * S.chan_stride, c1 = (long long)a.flip_chan[c] * S.chan_stride;
 #pragma unroll
-        for (int ki = 0; ki < KI; ki++) {
-            if (actl[ki]) {
+        for (int u = 0; u < kPostI_LD; u++) {
+            if (actl[u]) {
                 if (F16) {
                     const __half *p = static_cast<const __half *>(S.net);
-                    pv0[ki] = __half2float(p[g0[ki] + c0]);
-                    pv1[ki] = __half2float(p[g1[ki] + c1]);
+                    pv0[u] = __half2float(p[g0[u] + c0]);
+                    pv1[u] = __half2float(p[g1[u] + c1]);
                 } else {
                     const float *p = static_cast<const float *>(S.net);
-                    pv0[ki] = p[g0[ki] + c0];
-                    pv1[ki] = p[g1[ki] + c1];
+                    pv0[u] = p[g0[u] + c0];
+                    pv1[u] = p[g1[u] + c1];
                 }
             }
         }
     };
     const size_t plane = (size_t)a.H * a.W;
-    const int orow = a.W;
-    const size_t othread = (size_t)(oy0 + 4 * p2) * a.W + ox0 + X2;  // first output of item 0; item 1 is 16 rows below
-    if (c_begin < c_end) prefetch(c_begin);
-    int buf = 0;
-    for (int c = c_begin; c < c_end; c++, buf ^= 1) {
-        // ---- source tile: (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
+    const size_t othread = (size_t)(oy0 + 4 * p2) * a.W + ox0 + 4 * x2;  // first output of the pass-2 item
+    // One barrier per channel: the interval between two barriers runs the horizontal pass of channel c (source tile buffer
+    // `buf` -> s1[buf]), the vertical pass + stores of channel c - 1 (s1[buf ^ 1]), commits channel c + 1's source tile (loaded
+    // one interval ago) to the other s0 buffer and puts channel c + 2's loads in flight.
+    auto commit = [&](int b) {  // (out[c] + mirrored_out[flip(c)][:, ::-1]) / 2  (:139-140), float32
 #pragma unroll
-        for (int ki = 0; ki < KI; ki++)
-            if (actl[ki]) s0[(warp + NW * ki) * kPostI_S0 + lane] = __fdiv_rn(__fadd_rn(pv0[ki], pv1[ki]), 2.0f);
-        __syncthreads();
-        if (c + 1 < c_end) prefetch(c + 1);
-        // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
-        float *s1b = s1[buf];
-        if (act1) {
-            const float a0 = s0[h0], a1 = s0[h1], a2 = s0[h2], a3 = s0[h3], a4 = s0[h4];
-            float4 r;
+        for (int u = 0; u < kPostI_LD; u++)
+            if (actl[u]) s0[b][sdst[u]] = __fdiv_rn(__fadd_rn(pv0[u], pv1[u]), 2.0f);
+    };
+    if (c_begin < c_end) {
+        prefetch(c_begin);
+        commit(0);
+        if (c_begin + 1 < c_end) prefetch(c_begin + 1);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (int c = c_begin; c <= c_end; c++, buf ^= 1) {
+        // ---- pass 1: horizontal x4
+        if (act1 && c < c_end) {
+            const float a0 = s0[buf][h0], a1 = s0[buf][h1], a2 = s0[buf][h2], a3 = s0[buf][h3], a4 = s0[buf][h4], a5 = s0[buf][h5];
+            float4 r, t;
             r.x = tap4w(a0, a1, a2, a3, W0);
             r.y = tap4w(a0, a1, a2, a3, W1);
             r.z = tap4w(a1, a2, a3, a4, W2);
             r.w = tap4w(a1, a2, a3, a4, W3);
-            *reinterpret_cast<float4 *>(s1b + d1) = r;
+            t.x = tap4w(a1, a2, a3, a4, W0);
+            t.y = tap4w(a1, a2, a3, a4, W1);
+            t.z = tap4w(a2, a3, a4, a5, W2);
+            t.w = tap4w(a2, a3, a4, a5, W3);
+            *reinterpret_cast<float4 *>(s1[buf] + d1) = r;
+            *reinterpret_cast<float4 *>(s1[buf] + d1 + 4) = t;
         }
-        __syncthreads();
         // ---- pass 2: vertical x4, stored straight to the maps (single scale: avg = 0.0 + v / 1 is the float32 value itself)
-        const bool is_heat = c < a.K;
-        const size_t pbase = (is_heat ? ((size_t)n * a.K + c) * plane : ((size_t)n * (a.n_out - a.K) + (c - a.K)) * plane) + othread;
-        const bool store_f = is_heat || !a.paf_is_f64;
-        float *const of = (is_heat ? a.heat : static_cast<float *>(a.paf)) + pbase;
-        double *const od = static_cast<double *>(a.paf) + pbase;
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (!act2[u]) continue;
-            const float b0 = s1b[v0[u]], b1 = s1b[v1[u]], b2 = s1b[v2[u]], b3 = s1b[v3[u]], b4 = s1b[v4[u]];
-            float r[4];
-            r[0] = tap4w(b0, b1, b2, b3, W0);
-            r[1] = tap4w(b0, b1, b2, b3, W1);
-            r[2] = tap4w(b1, b2, b3, b4, W2);
-            r[3] = tap4w(b1, b2, b3, b4, W3);
+        if (act2 && c > c_begin) {
+            const float *s1b = s1[buf ^ 1];
+            const int cp = c - 1;
+            const float4 b0 = *reinterpret_cast<const float4 *>(s1b + v0), b1 = *reinterpret_cast<const float4 *>(s1b + v1),
+                         b2 = *reinterpret_cast<const float4 *>(s1b + v2), b3 = *reinterpret_cast<const float4 *>(s1b + v3),
+                         b4 = *reinterpret_cast<const float4 *>(s1b + v4);
+            float4 r[4];
+            r[0] = make_float4(tap4w(b0.x, b1.x, b2.x, b3.x, W0), tap4w(b0.y, b1.y, b2.y, b3.y, W0), tap4w(b0.z, b1.z, b2.z, b3.z, W0), tap4w(b0.w, b1.w, b2.w, b3.w, W0));
+            r[1] = make_float4(tap4w(b0.x, b1.x, b2.x, b3.x, W1), tap4w(b0.y, b1.y, b2.y, b3.y, W1), tap4w(b0.z, b1.z, b2.z, b3.z, W1), tap4w(b0.w, b1.w, b2.w, b3.w, W1));
+            r[2] = make_float4(tap4w(b1.x, b2.x, b3.x, b4.x, W2), tap4w(b1.y, b2.y, b3.y, b4.y, W2), tap4w(b1.z, b2.z, b3.z, b4.z, W2), tap4w(b1.w, b2.w, b3.w, b4.w, W2));
+            r[3] = make_float4(tap4w(b1.x, b2.x, b3.x, b4.x, W3), tap4w(b1.y, b2.y, b3.y, b4.y, W3), tap4w(b1.z, b2.z, b3.z, b4.z, W3), tap4w(b1.w, b2.w, b3.w, b4.w, W3));
             if (a.nan_scrub) {  // demo_image.py:179-180
 #pragma unroll
-                for (int k = 0; k < 4; k++) r[k] = r[k] != r[k] ? 0.0f : r[k];
+                for (int k = 0; k < 4; k++) {
+                    r[k].x = r[k].x != r[k].x ? 0.0f : r[k].x; r[k].y = r[k].y != r[k].y ? 0.0f : r[k].y;
+                    r[k].z = r[k].z != r[k].z ? 0.0f : r[k].z; r[k].w = r[k].w != r[k].w ? 0.0f : r[k].w;
+                }
             }
-            const int ybase = 4 * (p2 + 4 * u);  // tile row of r[0]
-            const size_t o = (size_t)(16 * u) * orow;
-            if (store_f) {
+            const bool is_heat = cp < a.K;
+            const size_t pbase = (is_heat ? ((size_t)n * a.K + cp) * plane : ((size_t)n * (a.n_out - a.K) + (cp - a.K)) * plane) + othread;
+            if (is_heat || !a.paf_is_f64) {
+                float *of = (is_heat ? a.heat : static_cast<float *>(a.paf)) + pbase;
+                if (vec) {
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (full || ybase + k < th) of[o + (size_t)k * orow] = r[k];
+                    for (int k = 0; k < 4; k++)
+                        if (4 * p2 + k < th) *reinterpret_cast<float4 *>(of + (size_t)k * a.W) = r[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (4 * p2 + k < th) {
+                            const float e[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+#pragma unroll
+                            for (int x = 0; x < 4; x++)
+                                if (4 * x2 + x < tw) of[(size_t)k * a.W + x] = e[x];
+                        }
+                    }
+                }
             } else {
+                double *od = static_cast<double *>(a.paf) + pbase;
+                if (vec) {
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (full || ybase + k < th) od[o + (size_t)k * orow] = (double)r[k];
+                    for (int k = 0; k < 4; k++) {
+                        if (4 * p2 + k < th) {
+                            double2 *q = reinterpret_cast<double2 *>(od + (size_t)k * a.W);
+                            q[0] = make_double2((double)r[k].x, (double)r[k].y);
+                            q[1] = make_double2((double)r[k].z, (double)r[k].w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (4 * p2 + k < th) {
+                            const float e[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+#pragma unroll
+                            for (int x = 0; x < 4; x++)
+                                if (4 * x2 + x < tw) od[(size_t)k * a.W + x] = (double)e[x];
+                        }
+                    }
+                }
             }
         }
-        // no barrier here: the next channel writes s0 (last read before this channel's second barrier) and the OTHER s1 buffer
+        if (c + 1 < c_end) {
+            commit(buf ^ 1);
+            if (c + 2 < c_end) prefetch(c + 2);
+        }
+        __syncthreads();
     }
 }
 

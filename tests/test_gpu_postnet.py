@@ -67,6 +67,8 @@ CASES = {
     "identity_128_to_512": ([(32, 40)], [(128, 160)], (128, 160)),
     "identity_odd": ([(19, 23)], [(75, 90)], (75, 90)),                    # the identity kernel's border tiles: sizes not multiples of 4
     "identity_tall": ([(40, 9)], [(160, 33)], (160, 33)),
+    "identity_wide": ([(12, 80)], [(45, 320)], (45, 320)),                 # full-width tiles with 16-byte stores, a partial tile row
+    "identity_wide_odd": ([(11, 70)], [(41, 277)], (41, 277)),             # a full tile followed by a partial one, W not a multiple of 4
     "padded_ratio_1.25": ([(32, 48)], [(120, 180)], (96, 144)),            # 640-style box: crop 120x180 of 128x192, image smaller
     "upscale_ratio_0.6": ([(16, 32)], [(60, 110)], (100, 183)),            # image larger than the network input
     "odd_sizes": ([(19, 23)], [(70, 89)], (131, 167)),
