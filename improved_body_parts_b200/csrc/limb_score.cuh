@@ -46,7 +46,10 @@ struct ScoreArgs {
 constexpr int kScoreThreads = 512;
 constexpr uint32_t kBulkChunkBytes = 32768;
 constexpr int kScreenMaxMid = 63;       // per-m tables (maxfail, sample positions, reciprocals)
-constexpr int kScreenSamples = 10;      // interior samples looked at per pair
+#ifndef SPG_SCREEN_SAMPLES
+#define SPG_SCREEN_SAMPLES 10
+#endif
+constexpr int kScreenSamples = SPG_SCREEN_SAMPLES;  // interior samples looked at per pair (build-time: `make variants` for the tuning sweep)
 constexpr int kScreenMaxDim = 2048;     // f32 error of a 1/64-px position stays << 1 unit up to this map size
 
 inline size_t score_smem_bytes(size_t plane_bytes, int capP) {

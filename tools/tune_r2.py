@@ -5,7 +5,10 @@ import itertools, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from improved_body_parts_b200 import skeleton, synth
+from improved_body_parts_b200 import grouping
 from improved_body_parts_b200.grouping import Grouper
+if os.environ.get("SPG_LIB"):   # a build variant (make variants / make trace), by path
+    grouping.LIB_PATH = os.environ["SPG_LIB"]
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 NB = 256
@@ -34,7 +37,10 @@ def measure(env):
     os.environ.update({k: str(v) for k, v in env.items()})
     g = Grouper(max_batch=NB, max_person_rows=64)
     g.group_device(hd, pd, 128, prm)
-    r = {"env": env,
+    dt = g.device_tensors()
+    surv = float(dt["surv_count"][:NB].float().mean().item())
+    cand = float(dt["cand_count"][:NB].float().mean().item())
+    r = {"env": env, "lib": os.path.basename(grouping.LIB_PATH), "survivors_per_item": round(surv, 1), "candidates_per_item": round(cand, 1),
          "nms": timeit(lambda: g.nms_peaks(hd, prm)), "score": timeit(lambda: g.limb_score(pd, 128, prm)),
          "match": timeit(lambda: g.limb_match(NB, prm)), "assemble": timeit(lambda: g.assemble(NB, prm)),
          "match_assemble": timeit(lambda: g.match_assemble(NB, prm)), "path": timeit(lambda: g.group_device(hd, pd, 128, prm))}
