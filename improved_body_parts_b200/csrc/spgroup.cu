@@ -25,6 +25,7 @@
 #include "match_assemble.cuh"
 #include "nms_peaks.cuh"
 #include "nms_peaks_persist.cuh"
+#include "nms_peaks_banded.cuh"
 #include "postnet.cuh"
 
 using namespace spg;
@@ -149,6 +150,19 @@ int launch_nms(spg_handle *h, const float *heat, int64_t img_stride, int64_t cha
         SPG_CUDA(h, cudaGetLastError());
         return SPG_OK;
     }
+    const NmsBanding bg = (h->persist && a.use_bulk) ? nms_banding(H, W, h->ws.capP, h->smem_optin - 1024) : NmsBanding{};
+    if (bg.slots >= kNmsBTeams) {
+        // planes that do not fit three times: the same roles over a ring of ~17 KB band slots, four scanner teams
+        const int items = n * h->ws.K;
+        a.band_rows = bg.band_rows;
+        SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_banded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg.smem));
+        nms_peaks_banded_kernel<<<std::min(items, h->sm_count), kNmsBThreads, bg.smem, st>>>(a, items, bg.slots, bg.n_bands);
+        h->stage_kernel[0] = "nms_peaks_banded_kernel";
+        h->launches++;
+        SPG_CUDA(h, cudaGetLastError());
+        return SPG_OK;
+    }
+    a.band_rows = std::max(4, std::min(H, 4096 / W));
     const size_t smem = nms_smem_bytes(a.band_rows, H, W, h->ws.capP);
     if (smem > h->smem_optin) return fail(h, SPG_E_INVALID, "map width %d needs %zu B of shared memory per band", W, smem);
     SPG_CUDA(h, cudaFuncSetAttribute(nms_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

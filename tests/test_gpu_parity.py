@@ -117,6 +117,27 @@ def test_unaligned_widths_take_the_generic_loaders(env, H, W):
         _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
 
 
+@pytest.mark.parametrize("H,W,persons", [(200, 260, 12), (150, 512, 10), (300, 132, 10)])
+def test_planes_too_large_for_the_plane_ring_take_the_banded_nms(env, H, W, persons):
+    """Keypoint planes that do not fit shared memory three times go through nms_peaks_banded_kernel: band heights that do
+    not divide H, a last band of a few rows, widths whose bands hold 15 / 8 / 31 rows -- peaks on band borders use the halo rows."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(2600 + H, 3, H, W, persons, scale_range=(1.5, 3.0), edge=True)
+    params = env.skeleton.default_params()
+    o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, H, params)
+    g = env.Grouper(max_batch=3, max_h=H, max_w=W)
+    try:
+        g.group_device(t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev), H, params)
+        r = g.fetch()
+        names = g.stage_kernels()
+    finally:
+        g.close()
+    assert names[0] == "nms_peaks_banded_kernel", names
+    assert (r.status == 0).all() and (o.status == 0).all()
+    for i in range(3):
+        _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
+
+
 def test_512_planes_sample_through_l2(env):
     """BASELINE.json configs[3] shape: 512x512 maps do not fit shared memory (1 MiB / plane)."""
     heat, paf = env.synth.make_batch(31337, 2, 512, 512, 24, scale_range=(3.0, 5.0))
