@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small run for compute-sanitizer (memcheck / synccheck): dirty images through every kernel of the library --
-post-network stage (single- and multi-scale, non-identity second resize), persistent and per-item nms / limb_score
+post-network stage (identity, single- and multi-scale, non-identity second resize), persistent, banded and per-item nms / limb_score
 (f32, f32-as-f64, f64), fused match+assemble with wire records and the armed signal, the stand-alone match / assemble."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -31,6 +31,12 @@ outs = [torch.from_numpy(np.stack([synth.make_network_output(5 + i, int(24 * f),
 g2 = Grouper(max_batch=2, max_h=160, max_w=200)
 h1, p1 = g2.postnet([outs[1]], [(90, 120)], (77, 101))
 h3, p3 = g2.postnet(outs, [(48, 64), (96, 128), (192, 256)], (96, 128))
+hi, pi = g2.postnet([outs[1]], [(96, 128)], (96, 128))             # crop == image: the identity kernel
 g2.group_device(h3, p3, 96, prm)
+# planes that do not fit shared memory three times: banded nms, body-part planes sampled through L2
+heat3, paf3 = synth.make_batch(7, 2, 150, 260, 8, scale_range=(1.5, 3.0), edge=True)
+g3 = Grouper(max_batch=2, max_h=150, max_w=260)
+g3.group_device(torch.from_numpy(heat3).to(dev), torch.from_numpy(paf3).to(dev), 150, prm)
+k3 = g3.stage_kernels()
 torch.cuda.synchronize()
-print("persons", r.n_persons.tolist(), "status", r.status.tolist(), "kernels", k1, g.stage_kernels(), "postnet", tuple(h1.shape), tuple(p3.shape))
+print("persons", r.n_persons.tolist(), "status", r.status.tolist(), "kernels", k1, g.stage_kernels(), "postnet", tuple(h1.shape), tuple(p3.shape), tuple(hi.shape), "large planes", k3)
