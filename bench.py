@@ -752,23 +752,34 @@ def run_pipeline(args, local_rank):
     plane = B * H * W
     if single:
         post_bytes = net_read + plane * (18 * 4 + 30 * 4)
-    else:  # float64 accumulators: written by every scale, read back by all but the first; float32 keypoint maps once
-        post_bytes = net_read + plane * 48 * 8 * ns + plane * 48 * 8 * (ns - 1) + plane * 18 * 4
+    else:
+        # the scale loop runs inside the kernel (groups of 4 scales): network outputs read once, float32 keypoint maps and
+        # float64 body-part maps written once; a further group of scales re-reads and re-writes the float64 sums
+        # (48 planes: the keypoint sums live in a float64 scratch until the last group)
+        groups = (ns + 3) // 4
+        post_bytes = net_read + plane * (18 * 4 + 30 * 8) + (groups - 1) * plane * 48 * 8 * 2
     alg = [None] * n_pre + [plane * 18 * 4, plane * 30 * esz, None]
     alg[n_pre - 1] = post_bytes
-    names = [nme for nme, _ in stages[:n_pre]] + [n for n in g.stage_kernels() if n][:3]
+    names = [g.postnet_kernel() if nme == "postnet_kernel" else nme for nme, _ in stages[:n_pre]] + [n for n in g.stage_kernels() if n][:3]
     kernels = {}
     for i, nme in enumerate(names):
         kernels[nme] = {"ms": stage_ms[i], "algorithmic_GBps": alg[i] / (stage_ms[i] * 1e-3) / 1e9 if alg[i] else None,
                         "frac_of_hbm_peak": alg[i] / (stage_ms[i] * 1e-3) / 1e9 / hbm_peak if alg[i] else None}
-        if nme == "postnet_kernel" and ns > 1:
-            kernels[nme]["launches_per_pass"] = ns
+        if nme.startswith("postnet") and ns > 4:
+            kernels[nme]["launches_per_pass"] = (ns + 3) // 4
         if nme == "imhn_forward":
             kernels[nme]["note"] = "cuDNN/cuBLAS library kernels inside one CUDA graph (imhn.Runner); not a kernel of this repo"
     dom = max(range(n_pre - 1, len(names)), key=lambda i: stage_ms[i])  # dominant kernel of THIS repo (the network is library code)
     ach = (alg[dom] or sum(a for a in alg if a)) / (stage_ms[dom] * 1e-3) / 1e9
+    traffic = None   # ncu capture of the same kernel on the same configuration (profiles/traffic.json), if there is one
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.config in ("net128", "512"):
+        tr = json.load(open(tpath))
+        suffix = "@512" if args.config == "512" else ""
+        hits = [v for k, v in tr.items() if k.split("<")[0] == names[dom].split("<")[0] and k.endswith(suffix) and ("@" in k) == bool(suffix)]
+        traffic = hits[-1] if hits else None
     roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom]}
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom]}
     result = {
         "metric": metric_name(args) + (" (from the images: network + post-network stage + grouping)" if runner else " (from the network output)"), "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "ms_per_pass": elapsed_ms / n_pass,

@@ -238,8 +238,13 @@ __global__ void __launch_bounds__(kPostThreads) postnet_generic_kernel(PostArgs 
 // pixels in registers while it works through the scales, so the averaged maps are written exactly once -- a launch per
 // scale would read-modify-write 48 float64 planes per extra scale (3.6x the traffic at 3 scales).
 // Same operations in the same order as the generic kernel: identical maps.
-constexpr int kPostF_C1 = 104, kPostF_R1 = 56;
+// Tile capacities of the stride-4 kernel: a full 64 x 32 output tile up to a second resize that halves the crop (the x2
+// scale of the reference's multi-scale search): 64 * 2 + 13 <= 144 intermediate columns, 32 * 2 + 13 <= 80 rows; the source
+// tile is a quarter of that plus the taps.  (The first version's 104 x 56 made the x2 scale cut the tile to 43 x 19: a third
+// of the lanes idle in the passes of the second resize, and the per-(channel, scale) set-up paid for 817 pixels instead of 2048.)
+constexpr int kPostF_C1 = 144, kPostF_R1 = 80;
 constexpr int kPostF_Q = kPostF_C1 / 4, kPostF_P = kPostF_R1 / 4;
+constexpr int kPostF_CS = 44, kPostF_RS = 28;   // source tile (network resolution)
 struct PostTabs {
     float4 w2x[kPostTW], w2y[kPostTH];   // weights of the second resize per output column / row of the tile
     int4 o2x[kPostTW], o2y[kPostTH];     // its four tap offsets: columns of s2 (elements), rows of s3 (elements, x kPostTW)
@@ -249,7 +254,7 @@ struct PostTabs {
     int rng[8];
 };
 constexpr size_t postF_smem_bytes(int n_tabs) {
-    return n_tabs * sizeof(PostTabs) + sizeof(float) * ((size_t)kPostRS * kPostCS + (size_t)kPostRS * kPostF_C1 +
+    return n_tabs * sizeof(PostTabs) + sizeof(float) * ((size_t)kPostF_RS * kPostF_CS + (size_t)kPostF_RS * kPostF_C1 +
                                                         (size_t)kPostF_R1 * kPostF_C1 + (size_t)kPostF_R1 * kPostTW);
 }
 
@@ -261,13 +266,13 @@ __device__ __forceinline__ float tap4w(float a0, float a1, float a2, float a3, c
 // IDENT: every fused scale's second resize is the identity (crop == image: weights (0,1,0,0)) -- passes 3 and 4 fall away.
 // F16: the network output is float16.
 template <bool SINGLE, bool IDENT, bool F16>
-__global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
+__global__ void __launch_bounds__(kPostThreads, 2) postnet_kernel(PostArgs a) {
     constexpr int kTabs = SINGLE ? 1 : kPostMaxScales;
     extern __shared__ __align__(16) unsigned char post_smem[];
     PostTabs *TT = reinterpret_cast<PostTabs *>(post_smem);
-    float *s0 = reinterpret_cast<float *>(post_smem + kTabs * sizeof(PostTabs));  // source tile, flip-averaged [RS][kPostCS]
-    float *s1 = s0 + kPostRS * kPostCS;                                   // after the horizontal x4 pass    [RS][kPostF_C1]
-    float *s2 = s1 + kPostRS * kPostF_C1;                                 // after the vertical x4 pass      [4P][kPostF_C1]
+    float *s0 = reinterpret_cast<float *>(post_smem + kTabs * sizeof(PostTabs));  // source tile, flip-averaged [RS][kPostF_CS]
+    float *s1 = s0 + kPostF_RS * kPostF_CS;                               // after the horizontal x4 pass    [RS][kPostF_C1]
+    float *s2 = s1 + kPostF_RS * kPostF_C1;                               // after the vertical x4 pass      [4P][kPostF_C1]
     float *s3 = s2 + kPostF_R1 * kPostF_C1;                               // after the 2nd resize's h. pass  [4P][kPostTW]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,8 +341,9 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
     const size_t plane = (size_t)a.H * a.W;
     const bool more_follow = a.scale_index + a.n_fused < a.n_scales;  // only with more than kPostMaxScales scales
 
-    constexpr int KI = (kPostRS + NW - 1) / NW;  // source rows per warp; a source tile row (<= 32 columns) is one lane each
-    float pv0[KI], pv1[KI];
+    constexpr int KI = (kPostF_RS + NW - 1) / NW;   // source rows per warp
+    constexpr int KJ = (kPostF_CS + 31) / 32;       // column passes per row
+    float pv0[KI][KJ], pv1[KI][KJ];
     auto prefetch = [&](int c, int t) {
         const PostScale &S = a.sc[t];
         const int sc_lo = TT[t].rng[4], CS = TT[t].rng[5], sr_lo = TT[t].rng[6], RS = TT[t].rng[7];
@@ -346,15 +352,19 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
 #pragma unroll
         for (int ki = 0; ki < KI; ki++) {
             const int i = warp + NW * ki;
-            if (i < RS && lane < CS) {
-                if (F16) {
-                    const __half *p = static_cast<const __half *>(S.net);
-                    pv0[ki] = __half2float(p[base0 + (long long)i * S.w + lane]);
-                    pv1[ki] = __half2float(p[base1 + (long long)i * S.w - lane]);
-                } else {
-                    const float *p = static_cast<const float *>(S.net);
-                    pv0[ki] = p[base0 + (long long)i * S.w + lane];
-                    pv1[ki] = p[base1 + (long long)i * S.w - lane];
+#pragma unroll
+            for (int kj = 0; kj < KJ; kj++) {
+                const int j = lane + 32 * kj;
+                if (i < RS && j < CS) {
+                    if (F16) {
+                        const __half *p = static_cast<const __half *>(S.net);
+                        pv0[ki][kj] = __half2float(p[base0 + (long long)i * S.w + j]);
+                        pv1[ki][kj] = __half2float(p[base1 + (long long)i * S.w - j]);
+                    } else {
+                        const float *p = static_cast<const float *>(S.net);
+                        pv0[ki][kj] = p[base0 + (long long)i * S.w + j];
+                        pv1[ki][kj] = p[base1 + (long long)i * S.w - j];
+                    }
                 }
             }
         }
@@ -392,7 +402,11 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
 #pragma unroll
             for (int ki = 0; ki < KI; ki++) {
                 const int i = warp + NW * ki;
-                if (i < RS && lane < CS) s0[i * kPostCS + lane] = __fdiv_rn(__fadd_rn(pv0[ki], pv1[ki]), 2.0f);
+#pragma unroll
+                for (int kj = 0; kj < KJ; kj++) {
+                    const int j = lane + 32 * kj;
+                    if (i < RS && j < CS) s0[i * kPostF_CS + j] = __fdiv_rn(__fadd_rn(pv0[ki][kj], pv1[ki][kj]), 2.0f);
+                }
             }
             __syncthreads();
             {
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
             }
             // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
             for (int i = warp; i < RS; i += NW) {
-                const float *row = s0 + i * kPostCS;
+                const float *row = s0 + i * kPostF_CS;
                 for (int q = lane; q < Q; q += 32) {
                     const int *o = T.o1x[q];
                     const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
@@ -432,12 +446,20 @@ __global__ void __launch_bounds__(kPostThreads, 3) postnet_kernel(PostArgs a) {
             // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs
             if (!IDENT && !identity) {
                 const int yr_lo = T.o2y[0].x / kPostTW, yr_hi = T.o2y[th - 1].w / kPostTW;
+                int4 ox[KX];     // this thread's columns are the same in every row: offsets and weights once per (channel, scale)
+                float4 wx[KX];
+#pragma unroll
+                for (int kx = 0; kx < KX; kx++) {
+                    const int x = min(lane + 32 * kx, tw - 1);
+                    ox[kx] = T.o2x[x];
+                    wx[kx] = T.w2x[x];
+                }
                 for (int Y = yr_lo + warp; Y <= yr_hi; Y += NW) {
                     const float *row = s2 + Y * kPostF_C1;
-                    for (int x = lane; x < tw; x += 32) {
-                        const int4 o = T.o2x[x];
-                        s3[Y * kPostTW + x] = tap4w(row[o.x], row[o.y], row[o.z], row[o.w], T.w2x[x]);
-                    }
+#pragma unroll
+                    for (int kx = 0; kx < KX; kx++)
+                        if (lane + 32 * kx < tw)
+                            s3[Y * kPostTW + lane + 32 * kx] = tap4w(row[ox[kx].x], row[ox[kx].y], row[ox[kx].z], row[ox[kx].w], wx[kx]);
                 }
                 __syncthreads();
             }

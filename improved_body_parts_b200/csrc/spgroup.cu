@@ -51,7 +51,7 @@ struct spg_handle {
     size_t heat_acc_elems = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     int64_t launches = 0;
-    const char *stage_kernel[4] = {"", "", "", ""};
+    const char *stage_kernel[5] = {"", "", "", "", ""};  // nms_peaks, limb_score, limb_match, assemble, post-network
     // tuning / A-B switches, read from the environment ONCE in spg_create (never per launch); none changes a result
     int persist = 1;      // persistent warp-specialised nms_peaks / limb_score when they apply (SPG_PERSIST=0 turns them off)
     int screen = 1;       // limb_score phase A on (SPG_NO_SCREEN=1 turns it off: every pair is evaluated exactly)
@@ -597,7 +597,7 @@ int spg_wire_wait(int32_t device, const uint64_t *word_dev, uint64_t value, void
 
 int64_t spg_launch_count(const spg_handle *h) { return h ? h->launches : 0; }
 
-const char *spg_stage_kernel(const spg_handle *h, int32_t stage) { return (h && stage >= 0 && stage < 4) ? h->stage_kernel[stage] : ""; }
+const char *spg_stage_kernel(const spg_handle *h, int32_t stage) { return (h && stage >= 0 && stage < 5) ? h->stage_kernel[stage] : ""; }
 
 // ---- post-network stage ------------------------------------------------------------------------
 int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, int32_t W, float *heat_out, void *paf_out,
@@ -673,8 +673,8 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
             a.tile_w = kPostTW; a.tile_h = kPostTH;
             for (int t = 0; t < a.n_fused; t++) {
                 a.sc[t] = scale_of(d->scales[t0 + t]);
-                a.tile_w = std::min(a.tile_w, tile_dim(a.sc[t].sx2, a.sx1, kPostF_C1, kPostCS, kPostTW, 13.0));
-                a.tile_h = std::min(a.tile_h, tile_dim(a.sc[t].sy2, a.sy1, kPostF_R1, kPostRS, kPostTH, 13.0));
+                a.tile_w = std::min(a.tile_w, tile_dim(a.sc[t].sx2, a.sx1, kPostF_C1, kPostF_CS, kPostTW, 13.0));
+                a.tile_h = std::min(a.tile_h, tile_dim(a.sc[t].sy2, a.sy1, kPostF_R1, kPostF_RS, kPostTH, 13.0));
             }
             a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
             a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
@@ -709,10 +709,13 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
                 dim3 grid_i((unsigned)(a.tiles_x * a.tiles_y), (unsigned)((a.n_out + a.chan_chunk - 1) / a.chan_chunk), (unsigned)n);
                 if (all16) postnet_x4_ident_kernel<true><<<grid_i, kPostThreads, 0, st>>>(a);
                 else postnet_x4_ident_kernel<false><<<grid_i, kPostThreads, 0, st>>>(a);
+                h->stage_kernel[4] = "postnet_x4_ident_kernel";
             } else if (single) {
+                h->stage_kernel[4] = "postnet_kernel";
                 if (ident) { if (all16) SPG_POST_LAUNCH(true, true, true); else SPG_POST_LAUNCH(true, true, false); }
                 else { if (all16) SPG_POST_LAUNCH(true, false, true); else SPG_POST_LAUNCH(true, false, false); }
             } else {
+                h->stage_kernel[4] = "postnet_kernel";
                 if (ident) { if (all16) SPG_POST_LAUNCH(false, true, true); else SPG_POST_LAUNCH(false, true, false); }
                 else { if (all16) SPG_POST_LAUNCH(false, false, true); else SPG_POST_LAUNCH(false, false, false); }
             }
@@ -735,6 +738,7 @@ int spg_postnet(spg_handle *h, const spg_postnet_desc *d, int32_t n, int32_t H, 
         a.chan_chunk = 1;
         dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)a.n_out, (unsigned)n);
         postnet_generic_kernel<<<grid, kPostThreads, 0, st>>>(a);
+        h->stage_kernel[4] = "postnet_generic_kernel";
         h->launches++;
         SPG_CUDA(h, cudaGetLastError());
     }

@@ -309,6 +309,10 @@ class Grouper:
         """Names of the kernel variants the last launches used: (nms_peaks, limb_score, limb_match, assemble)."""
         return tuple((self._lib.spg_stage_kernel(self._h, i) or b"").decode() for i in range(4))
 
+    def postnet_kernel(self) -> str:
+        """Name of the kernel the last ``postnet`` call launched."""
+        return (self._lib.spg_stage_kernel(self._h, 4) or b"").decode()
+
     # -- wire records (include/spgroup.h; wire.py is the host-side view) -------------------------------
     def wire_record_bytes(self, rows: Optional[int] = None) -> int:
         """Bytes of one image's record with ``rows`` person rows (default: ``max_person_rows``)."""
