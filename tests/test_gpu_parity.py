@@ -138,6 +138,32 @@ def test_planes_too_large_for_the_plane_ring_take_the_banded_nms(env, H, W, pers
         _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
 
 
+@pytest.mark.parametrize("capP,capR", [(37, 33), (50, 47)])
+def test_odd_capacities(env, capP, capR):
+    """Capacities that break the 16-byte granularity of the bulk copies (peak arrays of 18 x 37 floats, connection tables
+    of 30 x 37 words): the fused kernel's matchers stage the peaks themselves, the stand-alone assembler loads its tables
+    with plain loads; record / slot / scratch layouts with odd counts."""
+    t = env.torch
+    heat, paf = env.synth.make_batch(3737, 6, 128, 128, 14, drop_prob=0.1, edge=True, colocate=1)
+    params = env.skeleton.default_params()
+    o = env.so.group_batch(heat, paf, env.skeleton.LIMBS, 128, params)
+    hd, pd = t.from_numpy(heat).to(env.dev), t.from_numpy(paf).to(env.dev)
+    for fused in ("1", "0"):
+        os.environ["SPG_FUSE_MA"] = fused
+        try:
+            g = env.Grouper(max_batch=6, max_peaks_per_part=capP, max_person_rows=capR)
+        finally:
+            os.environ.pop("SPG_FUSE_MA", None)
+        try:
+            g.group_device(hd, pd, 128, params)
+            r = g.fetch()
+        finally:
+            g.close()
+        assert (r.status == 0).all() and (o.status == 0).all()
+        for i in range(6):
+            _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"fused={fused} image {i}")
+
+
 def test_512_planes_sample_through_l2(env):
     """BASELINE.json configs[3] shape: 512x512 maps do not fit shared memory (1 MiB / plane)."""
     heat, paf = env.synth.make_batch(31337, 2, 512, 512, 24, scale_range=(3.0, 5.0))

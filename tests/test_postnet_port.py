@@ -94,3 +94,15 @@ def test_post_network_stage_equals_the_reference_lines_with_cv2():
                                                 skeleton.FLIP_PAF_ORD, skeleton.FLIP_HEAT_ORD,
                                                 resize=lambda m, dsize, fx=0.0, fy=0.0: _cv(m, dict(dsize=dsize) if dsize else dict(fx=fx, fy=fy)))
     assert np.array_equal(same_heat, heat) and np.array_equal(same_paf, paf)
+
+
+def test_three_instruction_division_of_the_multi_scale_kernel_is_exact():
+    """csrc/postnet.cuh::div_by_scales replaces `map / n_scales` (evaluate.py:160-161) by a multiply and two FMAs; the
+    tool checks it against the correctly rounded quotient for every float32 significand (here: n = 3, one binade)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_div_by_scales.py")
+    spec = importlib.util.spec_from_file_location("check_div_by_scales", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check(3, binades=(127,), sample=300) == 0
