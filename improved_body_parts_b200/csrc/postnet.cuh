@@ -430,33 +430,51 @@ __global__ void __launch_bounds__(kPostThreads, 2) postnet_kernel(PostArgs a) {
                 if (tn == a.n_fused) { tn = 0; cn = c + 1; }
                 if (cn < c_end) prefetch(cn, tn);
             }
-            // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out
-            for (int i = warp; i < RS; i += NW) {
+            // ---- pass 1: horizontal x4 -- five source values in, four intermediate columns out.  A row's groups beyond the
+            // 32nd (Q <= 36: the x2 scale has 35) do not get a second lane pass of their own: all rows' leftovers are dealt
+            // to the CTA's threads four per row.
+            auto h_item = [&](int i, int q) {
                 const float *row = s0 + i * kPostF_CS;
-                for (int q = lane; q < Q; q += 32) {
-                    const int *o = T.o1x[q];
-                    const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
-                    float4 r;
-                    r.x = tap4w(v0, v1, v2, v3, W0);
-                    r.y = tap4w(v0, v1, v2, v3, W1);
-                    r.z = tap4w(v1, v2, v3, v4, W2);
-                    r.w = tap4w(v1, v2, v3, v4, W3);
-                    *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = r;
-                }
+                const int *o = T.o1x[q];
+                const float v0 = row[o[0]], v1 = row[o[1]], v2 = row[o[2]], v3 = row[o[3]], v4 = row[o[4]];
+                float4 r;
+                r.x = tap4w(v0, v1, v2, v3, W0);
+                r.y = tap4w(v0, v1, v2, v3, W1);
+                r.z = tap4w(v1, v2, v3, v4, W2);
+                r.w = tap4w(v1, v2, v3, v4, W3);
+                *reinterpret_cast<float4 *>(s1 + i * kPostF_C1 + 4 * q) = r;
+            };
+            for (int i = warp; i < RS; i += NW)
+                if (lane < Q) h_item(i, lane);
+            if (Q > 32) {
+                static_assert(kPostF_Q <= 36 && kPostF_RS * 4 <= kPostThreads, "leftover groups: four per row, one thread each");
+                const int i = tid >> 2, q = 32 + (tid & 3);
+                if (i < RS && q < Q) h_item(i, q);
             }
             __syncthreads();
-            // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157)
-            for (int p = warp; p < P; p += NW) {
+            // ---- pass 2: vertical x4 -> the cropped intermediate (what the reference holds after :148 / :157): five 16-byte
+            // loads in, four rows of four columns out
+            auto v_item = [&](int p, int x4) {
                 const int *o = T.o1y[p];
-                const int r0 = o[0], r1 = o[1], r2 = o[2], r3 = o[3], r4 = o[4];
-                float *dst = s2 + 4 * p * kPostF_C1;
-                for (int X = lane; X < C1; X += 32) {
-                    const float v0 = s1[r0 + X], v1 = s1[r1 + X], v2 = s1[r2 + X], v3 = s1[r3 + X], v4 = s1[r4 + X];
-                    dst[X] = tap4w(v0, v1, v2, v3, W0);
-                    dst[kPostF_C1 + X] = tap4w(v0, v1, v2, v3, W1);
-                    dst[2 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W2);
-                    dst[3 * kPostF_C1 + X] = tap4w(v1, v2, v3, v4, W3);
-                }
+                const float4 b0 = *reinterpret_cast<const float4 *>(s1 + o[0] + 4 * x4), b1 = *reinterpret_cast<const float4 *>(s1 + o[1] + 4 * x4),
+                             b2 = *reinterpret_cast<const float4 *>(s1 + o[2] + 4 * x4), b3 = *reinterpret_cast<const float4 *>(s1 + o[3] + 4 * x4),
+                             b4 = *reinterpret_cast<const float4 *>(s1 + o[4] + 4 * x4);
+                float *dst = s2 + 4 * p * kPostF_C1 + 4 * x4;
+                *reinterpret_cast<float4 *>(dst) = make_float4(tap4w(b0.x, b1.x, b2.x, b3.x, W0), tap4w(b0.y, b1.y, b2.y, b3.y, W0),
+                                                               tap4w(b0.z, b1.z, b2.z, b3.z, W0), tap4w(b0.w, b1.w, b2.w, b3.w, W0));
+                *reinterpret_cast<float4 *>(dst + kPostF_C1) = make_float4(tap4w(b0.x, b1.x, b2.x, b3.x, W1), tap4w(b0.y, b1.y, b2.y, b3.y, W1),
+                                                                           tap4w(b0.z, b1.z, b2.z, b3.z, W1), tap4w(b0.w, b1.w, b2.w, b3.w, W1));
+                *reinterpret_cast<float4 *>(dst + 2 * kPostF_C1) = make_float4(tap4w(b1.x, b2.x, b3.x, b4.x, W2), tap4w(b1.y, b2.y, b3.y, b4.y, W2),
+                                                                               tap4w(b1.z, b2.z, b3.z, b4.z, W2), tap4w(b1.w, b2.w, b3.w, b4.w, W2));
+                *reinterpret_cast<float4 *>(dst + 3 * kPostF_C1) = make_float4(tap4w(b1.x, b2.x, b3.x, b4.x, W3), tap4w(b1.y, b2.y, b3.y, b4.y, W3),
+                                                                               tap4w(b1.z, b2.z, b3.z, b4.z, W3), tap4w(b1.w, b2.w, b3.w, b4.w, W3));
+            };
+            for (int p = warp; p < P; p += NW)
+                if (lane < Q) v_item(p, lane);
+            if (Q > 32) {
+                static_assert(kPostF_P * 4 <= kPostThreads, "leftover column groups: four per row group, one thread each");
+                const int p = tid >> 2, x4 = 32 + (tid & 3);
+                if (p < P && x4 < Q) v_item(p, x4);
             }
             __syncthreads();
             // ---- pass 3: horizontal pass of the second resize over the crop rows the tile needs
