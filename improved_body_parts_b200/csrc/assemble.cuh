@@ -395,19 +395,19 @@ __device__ __forceinline__ void emit_people(const AssembleArgs &a, const PersonT
     const int WR = 2 * J + 2;  // x,y per joint, person score, presence mask
     const bool wire_on = ws.wire != nullptr && (size_t)min(ws.wire_rows, capR) * WR * sizeof(double) <= stage_bytes;
     double *s_wire = s_stage;
-    int *keep_pos = t.postA;  // 0: dropped, 1: kept, p + 2: kept at output position p
+    int *keep = t.postA;      // 1: the row survives the prune
+    int *keep_pos = t.postB;  // 0: dropped, p + 2: kept at output position p
     // keep flags and person scores: one row per thread (the two float64 divisions are ~100 instructions each)
     for (int j = tid; j < nrows; j += nthreads) {
         const RowRec r = load_row(t.row + j);
-        bool keep = false;
-        if (r.alive) keep = !(r.cnt < a.min_parts || __ddiv_rn(r.total, (double)r.cnt) < a.min_mean_score);
-        keep_pos[j] = keep ? 1 : 0;
-        if (keep) t.pscore[j] = __dsub_rn(1.0, __ddiv_rn(1.0, r.total));  // :541
+        bool kp = false;
+        if (r.alive) kp = !(r.cnt < a.min_parts || __ddiv_rn(r.total, (double)r.cnt) < a.min_mean_score);
+        keep[j] = kp ? 1 : 0;
+        if (kp) t.pscore[j] = __dsub_rn(1.0, __ddiv_rn(1.0, r.total));  // :541
     }
     if (tid == 0) *s_out = 0;
     __syncthreads();
     // A kept row's output position = number of kept rows born earlier: four threads per row, a quarter of the rows each.
-    // keep_pos goes from 1 to position + 2 while other threads still read it as a keep flag: non-zero either way.
     const int rows_per_pass = nthreads >> 2;
     for (int base = 0; base < nrows; base += rows_per_pass) {
         const int j = base + (tid >> 2), q = tid & 3;
@@ -416,7 +416,7 @@ __device__ __forceinline__ void emit_people(const AssembleArgs &a, const PersonT
         int o = 0, kept = 0;
         if (act)
             for (int u = q; u < nrows; u += 4) {
-                const bool ku = keep_pos[u] != 0;
+                const bool ku = keep[u] != 0;
                 kept += ku ? 1 : 0;
                 o += (ku && t.row[u].birth < mine) ? 1 : 0;
             }
@@ -425,7 +425,7 @@ __device__ __forceinline__ void emit_people(const AssembleArgs &a, const PersonT
         kept += __shfl_xor_sync(0xffffffffu, kept, 1);
         kept += __shfl_xor_sync(0xffffffffu, kept, 2);
         if (act && q == 0) {
-            if (keep_pos[j] != 0) keep_pos[j] = o + 2;
+            keep_pos[j] = keep[j] != 0 ? o + 2 : 0;
             if (j == 0) *s_out = kept;
         }
     }
