@@ -138,7 +138,7 @@ def test_planes_too_large_for_the_plane_ring_take_the_banded_nms(env, H, W, pers
         _assert_same(o.as_reference_structures(i), r.as_reference_structures(i), f"image {i}")
 
 
-@pytest.mark.parametrize("capP,capR", [(37, 33), (50, 47)])
+@pytest.mark.parametrize("capP,capR", [(37, 41), (50, 47)])
 def test_odd_capacities(env, capP, capR):
     """Capacities that break the 16-byte granularity of the bulk copies (peak arrays of 18 x 37 floats, connection tables
     of 30 x 37 words): the fused kernel's matchers stage the peaks themselves, the stand-alone assembler loads its tables
