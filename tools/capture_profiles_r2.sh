@@ -32,6 +32,7 @@ python tools/dropin_latency.py 512 14 > $out/dropin_latency_512.json 2>> $out/dr
 for t in memcheck synccheck; do
   compute-sanitizer --tool $t python tools/sanitize_run.py > $out/sanitizer_$t.txt 2>&1
 done
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $out/smoke.txt 2>&1
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/gpu.csv
 lscpu | grep -E "Model name|^CPU\(s\)" > $out/cpu.txt
 ls -la $out
